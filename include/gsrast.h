@@ -1,0 +1,192 @@
+/*
+ * gsrast.h -- C ABI of libgsrast.so, the sm_100a Gaussian-splat rasterizer.
+ *
+ * This header is the drop-in boundary for the hot path of jkulhanek/wild-gaussians:
+ * it replaces the C++ entry points the reference's pybind11 module binds
+ *   CudaRasterizer::Rasterizer::forward      (DGR/cuda_rasterizer/rasterizer.h:31-57,  rasterizer_impl.cu:198-340)
+ *   CudaRasterizer::Rasterizer::backward     (DGR/cuda_rasterizer/rasterizer.h:59-88,  rasterizer_impl.cu:344-444)
+ *   CudaRasterizer::Rasterizer::markVisible  (DGR/cuda_rasterizer/rasterizer.h:24-29,  rasterizer_impl.cu:141-153)
+ * (DGR = submodules/diff-gaussian-rasterization) and is what
+ *   RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA / markVisible  (DGR/rasterize_points.cu:35-225)
+ * would call instead.  Plain C: raw device pointers, ints and floats, an opaque stream
+ * handle (a cudaStream_t passed as void*), no torch types, no exceptions, no allocation
+ * inside the library.  Every function returns 0 on success, a positive cudaError_t or a
+ * negative GSR_E_* code on failure; gsr_last_error() then holds a thread-local message.
+ *
+ * All tensors are contiguous fp32 (ints where stated) on the current CUDA device.
+ * "absent" optional inputs are NULL (the reference's zero-element tensors,
+ * DGR/diff_gaussian_rasterization/__init__.py:218-228).
+ *
+ * Buffer protocol (replaces the reference's three std::function<char*(size_t)> resize
+ * callbacks, rasterize_points.cu:27-33,78-80):
+ *   1. gsr_forward_sizes()     -> bytes for geom_buffer and img_buffer      (caller allocates)
+ *   2. gsr_forward_geometry()  -> per-Gaussian projection, depth ordering, instance count R
+ *                                  (one stream sync, like rasterizer_impl.cu:283-284)
+ *   3. gsr_binning_sizes(R)    -> bytes for binning_buffer and the transient scratch
+ *   4. gsr_forward_render()    -> tile binning + per-tile front-to-back composite
+ * gsr_forward() does 1-4 in one call through a C allocation callback.
+ * geom/binning/img buffers must be kept (unmodified) for gsr_backward(); scratch may be
+ * released as soon as gsr_forward_render() has been enqueued (stream-ordered allocators) or
+ * completed.
+ */
+#ifndef GSRAST_H_INCLUDED
+#define GSRAST_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_ABI_VERSION 1
+
+/* negative status codes (positive values are cudaError_t) */
+#define GSR_E_INVALID      (-1)  /* bad argument (NULL where required, P<0, ...)            */
+#define GSR_E_PREFILTERED  (-2)  /* a Gaussian was culled although prefiltered=1
+                                    (reference: printf + __trap, auxiliary.h:156-160)        */
+#define GSR_E_CHANNELS     (-3)  /* reserved: non-RGB without colors_precomp
+                                    (rasterizer_impl.cu:244-247); this build is RGB only     */
+#define GSR_E_OVERFLOW     (-4)  /* instance count does not fit the supplied buffers         */
+
+/* which buffer an allocation callback is asked for */
+#define GSR_BUF_GEOM     0
+#define GSR_BUF_BINNING  1
+#define GSR_BUF_IMG      2
+#define GSR_BUF_SCRATCH  3
+
+/* Allocation callback for gsr_forward(): must return a device pointer to at least `bytes`
+ * bytes, 256-byte aligned, valid at least until gsr_backward() for GEOM/BINNING/IMG.     */
+typedef void* (*gsr_alloc_fn)(void* ctx, int which, size_t bytes);
+
+/* Inputs of one forward rasterization.  Field meaning follows
+ * CudaRasterizer::Rasterizer::forward (rasterizer_impl.cu:198-225).                        */
+typedef struct GsrForwardArgs {
+    int P;                        /* number of Gaussians                                    */
+    int D;                        /* active SH degree (0..3); ignored with colors_precomp   */
+    int M;                        /* SH coefficients per Gaussian, (deg_max+1)^2; 0 if none */
+    int W, H;                     /* image size in pixels                                   */
+    const float* background;      /* [3]                                                    */
+    const float* means3D;         /* [P,3]                                                  */
+    const float* shs;             /* [P,M,3] or NULL                                        */
+    const float* colors_precomp;  /* [P,3]   or NULL (exactly one of shs/colors_precomp)    */
+    const float* opacities;       /* [P] (or [P,1])                                         */
+    const float* scales;          /* [P,3]   or NULL                                        */
+    float        scale_modifier;
+    const float* rotations;       /* [P,4] (r,x,y,z), used un-normalised; or NULL           */
+    const float* cov3D_precomp;   /* [P,6]   or NULL (exactly one of scales+rot / cov3D)    */
+    const float* viewmatrix;      /* [16] row-vector convention (translation at 12..14)     */
+    const float* projmatrix;      /* [16] view*proj, same convention                        */
+    const float* campos;          /* [3]                                                    */
+    float tan_fovx, tan_fovy;
+    float kernel_size;            /* Mip-Splatting 2D low-pass (forward.cu:108-121)         */
+    const float* subpixel_offset; /* [H,W,2]                                                */
+    int prefiltered;
+    int debug;                    /* !=0: synchronise + check after every stage             */
+    /* Screen-space shard (multi-GPU tile-row partition): only tile rows
+     * [tile_y0, tile_y1) are binned and composited; pixels of other rows are not written.
+     * tile_y0 = tile_y1 = 0 means the whole image.                                         */
+    int tile_y0, tile_y1;
+    /* outputs */
+    float* out_color;             /* [3,H,W]  (rows of the shard are written)               */
+    int*   radii;                 /* [P]      screen radius in px, 0 = not rendered         */
+} GsrForwardArgs;
+
+/* Inputs/outputs of the backward pass.  Field meaning follows
+ * CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:344-377).
+ * Every output array is written completely by the call (zeros for Gaussians that were not
+ * rendered): no pre-zeroing is required, unlike rasterize_points.cu:157-165.               */
+typedef struct GsrBackwardArgs {
+    int P, D, M;
+    int R;                        /* num_rendered returned by the forward                   */
+    int W, H;
+    const float* background;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* scales;
+    float        scale_modifier;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    float tan_fovx, tan_fovy;
+    float kernel_size;
+    const float* subpixel_offset;
+    const int*   radii;           /* [P] from the forward                                   */
+    const void*  geom_buffer;
+    const void*  binning_buffer;
+    const void*  img_buffer;
+    const float* dL_dpix;         /* [3,H,W] upstream gradient of out_color                 */
+    int debug;
+    int tile_y0, tile_y1;         /* same shard as the forward                              */
+    void*  accum_scratch;         /* gsr_backward_scratch_bytes(P) bytes, need not be zeroed */
+    /* outputs */
+    float* dL_dmean2D;            /* [P,3]  x,y: NDC-scaled screen grad; z: sum |gx|+|gy|
+                                     (backward.cu:590-595)                                  */
+    float* dL_dconic;             /* [P,4]  (x,y,-,w) as backward.cu:598-600; may be NULL   */
+    float* dL_dopacity;           /* [P]                                                    */
+    float* dL_dcolor;             /* [P,3]                                                  */
+    float* dL_dmean3D;            /* [P,3]                                                  */
+    float* dL_dcov3D;             /* [P,6]; may be NULL when cov3D_precomp is NULL          */
+    float* dL_dsh;                /* [P,M,3]; required iff shs != NULL                      */
+    float* dL_dscale;             /* [P,3];  required iff scales != NULL                    */
+    float* dL_drot;               /* [P,4];  required iff rotations != NULL                 */
+} GsrBackwardArgs;
+
+/* Counters of the last forward on this geom buffer (device->host copied on request).     */
+typedef struct GsrStats {
+    int      num_rendered;        /* R: (Gaussian, tile) instances                          */
+    int      num_visible;         /* V: Gaussians with radii > 0                            */
+    int      num_tiles;           /* tiles in the shard                                     */
+    int      reserved;
+} GsrStats;
+
+int         gsr_abi_version(void);
+const char* gsr_last_error(void);
+
+/* -- forward ----------------------------------------------------------------------------- */
+int gsr_forward_sizes(int P, int M, int W, int H, size_t* geom_bytes, size_t* img_bytes);
+int gsr_forward_geometry(const GsrForwardArgs* args, void* geom_buffer, void* img_buffer,
+                         void* stream, int* num_rendered);
+int gsr_binning_sizes(int P, int W, int H, int num_rendered,
+                      size_t* binning_bytes, size_t* scratch_bytes);
+int gsr_forward_render(const GsrForwardArgs* args, void* geom_buffer, void* img_buffer,
+                       void* binning_buffer, void* scratch, int num_rendered, void* stream);
+int gsr_forward(const GsrForwardArgs* args, gsr_alloc_fn alloc, void* alloc_ctx,
+                void* stream, int* num_rendered);
+
+/* Re-composite with different per-Gaussian colours on the SAME geometry/binning state
+ * (wild-gaussians renders raw + appearance-toned colours per step, method.py:1573-1611).
+ * Writes out_color (and final_T / n_contrib into img_buffer2, sized like img_buffer).     */
+int gsr_forward_recolor(const GsrForwardArgs* args, const void* geom_buffer,
+                        const void* binning_buffer, const void* img_buffer,
+                        void* img_buffer2, void* stream);
+
+/* -- backward ---------------------------------------------------------------------------- */
+size_t gsr_backward_scratch_bytes(int P);
+int    gsr_backward(const GsrBackwardArgs* args, void* stream);
+
+/* -- markVisible (rasterizer_impl.cu:54-66,141-153): present[i] = (view*p).z > 0.2 ------- */
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* -- introspection used by parity tests and the benchmark -------------------------------- */
+/* accum_alpha (= final transmittance T per pixel, [H,W] f32) lives at the first
+ * 128-byte-aligned address of img_buffer, as in the reference ImageState
+ * (rasterizer_impl.cu:172-178; read by __init__.py:101-113).                               */
+int gsr_img_views(const void* img_buffer, int W, int H,
+                  const float** final_T, const uint32_t** n_contrib, const uint32_t** ranges /* uint2[T] */);
+/* sorted (tile-major, depth-minor) Gaussian index list, R entries                          */
+int gsr_binning_views(const void* binning_buffer, int num_rendered, const uint32_t** point_list);
+/* per-Gaussian projected state: depths f32[P], packed records float4[2P]
+ * {x, y, conic.x, conic.y | conic.z, opacity*coef, 0, 0}, tiles_touched u32[P], rgb f32[3P] */
+int gsr_geom_views(const void* geom_buffer, int P, int M, const float** depths,
+                   const float** records, const uint32_t** tiles_touched, const float** rgb);
+int gsr_get_stats(const void* geom_buffer, int P, int M, void* stream, GsrStats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSRAST_H_INCLUDED */

@@ -1,0 +1,410 @@
+// api.cu -- the extern "C" boundary of libgsrast.so (declared in include/gsrast.h) and the
+// forward / backward orchestration.  Replaces CudaRasterizer::Rasterizer::{forward,backward,
+// markVisible} (rasterizer_impl.cu:141-153,198-444) and the buffer carving of
+// rasterizer_impl.h:21-73.  All work is enqueued on the caller's stream; the only host
+// synchronisation is the read-back of the instance count R (the reference blocks on the same
+// value, rasterizer_impl.cu:283-284).
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace gsr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return (int)e;
+}
+
+// ---- carving -------------------------------------------------------------------------------
+template <typename T>
+static void take(char*& cur, T*& ptr, size_t count, size_t align = 256) {
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(cur) + align - 1) & ~(uintptr_t)(align - 1);
+    ptr = reinterpret_cast<T*>(a);
+    cur = reinterpret_cast<char*>(ptr + count);
+}
+
+size_t carve_geom(char* base, int P, int M, GeomState* out) {
+    GeomState g;
+    char* cur = base;
+    const size_t n = (size_t)P;
+    take(cur, g.rec, 2 * n);
+    take(cur, g.rgb, M > 0 ? 3 * n : 0);
+    take(cur, g.clamped, M > 0 ? n : 0);
+    take(cur, g.depths, n);
+    take(cur, g.tiles_touched, n);
+    take(cur, g.rect, n);
+    take(cur, g.counters, 8);
+    take(cur, g.key_a, n);
+    take(cur, g.key_b, n);
+    take(cur, g.val_a, n);
+    take(cur, g.val_b, n);
+    g.order = g.val_a;   // 32 key bits = 4 passes (even): the sorted pairs end up in (key_a, val_a)
+    take(cur, g.offsets, n + 1);
+    g.radix_tmp_count = radix_tmp_elems(n) + scan_tmp_elems(n);
+    take(cur, g.radix_tmp, g.radix_tmp_count);
+    if (out) *out = g;
+    return (size_t)(cur - base) + 256;
+}
+
+size_t carve_img(char* base, int W, int H, ImgState* out) {
+    ImgState im;
+    char* cur = base;
+    const size_t N = (size_t)W * H;
+    const size_t T = (size_t)tiles_x(W) * tiles_y(H);
+    take(cur, im.final_T, N, 128);   // first 128-B aligned field, like the reference ImageState
+    take(cur, im.n_contrib, N);
+    take(cur, im.ranges, T);
+    if (out) *out = im;
+    return (size_t)(cur - base) + 256;
+}
+
+size_t carve_bin(char* base, size_t R, BinState* out) {
+    BinState b;
+    char* cur = base;
+    take(cur, b.point_list, R);
+    take(cur, b.tile_keys, R);
+    if (out) *out = b;
+    return (size_t)(cur - base) + 256;
+}
+
+size_t carve_bin_scratch(char* base, size_t R, BinScratch* out) {
+    BinScratch b;
+    char* cur = base;
+    take(cur, b.key, R);
+    take(cur, b.val, R);
+    b.radix_tmp_count = radix_tmp_elems(R);
+    take(cur, b.radix_tmp, b.radix_tmp_count);
+    if (out) *out = b;
+    return (size_t)(cur - base) + 256;
+}
+
+static int num_bits(uint32_t n) {   // bits needed to represent values 0..n-1
+    int b = 0;
+    while (b < 32 && (1ull << b) < (unsigned long long)n) ++b;
+    return b;
+}
+
+static int check_fwd_args(const GsrForwardArgs* a) {
+    if (!a) { set_error("args is NULL"); return GSR_E_INVALID; }
+    if (a->P < 0 || a->W <= 0 || a->H <= 0) { set_error("bad sizes P=%d W=%d H=%d", a->P, a->W, a->H); return GSR_E_INVALID; }
+    if (a->P > 0) {
+        if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->background || !a->subpixel_offset ||
+            !a->out_color || !a->radii) { set_error("a required pointer is NULL"); return GSR_E_INVALID; }
+        if ((a->shs == nullptr) == (a->colors_precomp == nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return GSR_E_INVALID; }
+        const bool have_sr = a->scales != nullptr && a->rotations != nullptr;
+        if (have_sr == (a->cov3D_precomp != nullptr) || ((a->scales != nullptr) != (a->rotations != nullptr))) {
+            set_error("provide exactly one of (scales, rotations) / cov3D_precomp");
+            return GSR_E_INVALID;
+        }
+        if (a->shs && (a->M <= 0 || !a->campos)) { set_error("shs given but M<=0 or campos NULL"); return GSR_E_INVALID; }
+        if (a->shs && (a->D < 0 || a->D > 3 || (a->D + 1) * (a->D + 1) > a->M)) { set_error("SH degree %d does not fit M=%d", a->D, a->M); return GSR_E_INVALID; }
+    }
+    if (tiles_x(a->W) > 65535 || tiles_y(a->H) > 65535) { set_error("image too large"); return GSR_E_INVALID; }
+    return 0;
+}
+
+static void shard_rows(int H, int ty0_in, int ty1_in, int* ty0, int* ty1) {
+    const int gy = tiles_y(H);
+    if (ty0_in == 0 && ty1_in == 0) { *ty0 = 0; *ty1 = gy; return; }
+    *ty0 = ty0_in < 0 ? 0 : (ty0_in > gy ? gy : ty0_in);
+    *ty1 = ty1_in < *ty0 ? *ty0 : (ty1_in > gy ? gy : ty1_in);
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+const char* gsr_last_error(void) { return g_err; }
+
+int gsr_forward_sizes(int P, int M, int W, int H, size_t* geom_bytes, size_t* img_bytes) {
+    if (P < 0 || W <= 0 || H <= 0 || M < 0) { set_error("bad sizes"); return GSR_E_INVALID; }
+    if (geom_bytes) *geom_bytes = carve_geom(nullptr, P, M, nullptr);
+    if (img_bytes) *img_bytes = carve_img(nullptr, W, H, nullptr);
+    return 0;
+}
+
+int gsr_binning_sizes(int P, int W, int H, int num_rendered, size_t* binning_bytes, size_t* scratch_bytes) {
+    (void)P; (void)W; (void)H;
+    if (num_rendered < 0) { set_error("bad num_rendered"); return GSR_E_INVALID; }
+    if (binning_bytes) *binning_bytes = carve_bin(nullptr, (size_t)num_rendered, nullptr);
+    if (scratch_bytes) *scratch_bytes = carve_bin_scratch(nullptr, (size_t)num_rendered, nullptr);
+    return 0;
+}
+
+int gsr_forward_geometry(const GsrForwardArgs* a, void* geom_buffer, void* img_buffer, void* stream, int* num_rendered) {
+    (void)img_buffer;
+    int rc = check_fwd_args(a);
+    if (rc) return rc;
+    if (!num_rendered) { set_error("num_rendered is NULL"); return GSR_E_INVALID; }
+    *num_rendered = 0;
+    if (a->P == 0) return 0;
+    if (!geom_buffer) { set_error("geom_buffer is NULL"); return GSR_E_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool dbg = a->debug != 0;
+    GeomState g;
+    carve_geom((char*)geom_buffer, a->P, a->M, &g);
+    int ty0, ty1;
+    shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
+
+    GSR_CUDA(cudaMemsetAsync(g.counters, 0, 8 * sizeof(int32_t), s));
+    rc = launch_preprocess_fwd(*a, g, ty0, ty1, s);
+    if (rc) return rc;
+    GSR_STAGE(s, dbg, "preprocess_fwd_kernel");
+
+    // front-to-back order of the Gaussians: stable sort on the depth bits (all 32, u32 compare
+    // like the reference's key, rasterizer_impl.cu:104); culled ones carry 0xFFFFFFFF.
+    rc = radix_sort_pairs(g.key_a, g.val_a, g.key_b, g.val_b, (size_t)a->P, 0, 32, g.radix_tmp, s, dbg);
+    if (rc) return rc;
+
+    // instance offsets in depth order; offsets[P] = R
+    rc = scan_gathered(g.tiles_touched, g.order, g.offsets, (size_t)a->P, g.radix_tmp + radix_tmp_elems((size_t)a->P), s);
+    if (rc) return rc;
+    GSR_STAGE(s, dbg, "scan_gathered");
+
+    uint32_t R = 0;
+    int32_t counters[8];
+    GSR_CUDA(cudaMemcpyAsync(&R, g.offsets + a->P, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA(cudaMemcpyAsync(counters, g.counters, sizeof(counters), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA(cudaStreamSynchronize(s));
+    if (counters[0] != 0) {
+        set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
+        return GSR_E_PREFILTERED;
+    }
+    if (R > 0x7FFFFFFFu) { set_error("instance count %u overflows int", R); return GSR_E_OVERFLOW; }
+    GSR_CUDA(cudaMemcpyAsync(g.counters + 2, &R, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    *num_rendered = (int)R;
+    return 0;
+}
+
+int gsr_forward_render(const GsrForwardArgs* a, void* geom_buffer, void* img_buffer, void* binning_buffer, void* scratch,
+                       int num_rendered, void* stream) {
+    int rc = check_fwd_args(a);
+    if (rc) return rc;
+    if (a->P == 0) return 0;
+    if (!geom_buffer || !img_buffer || (num_rendered > 0 && (!binning_buffer || !scratch))) {
+        set_error("a buffer is NULL");
+        return GSR_E_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool dbg = a->debug != 0;
+    GeomState g;
+    ImgState im;
+    BinState b;
+    BinScratch bs;
+    carve_geom((char*)geom_buffer, a->P, a->M, &g);
+    carve_img((char*)img_buffer, a->W, a->H, &im);
+    const size_t R = (size_t)num_rendered;
+    carve_bin((char*)binning_buffer, R, &b);
+    carve_bin_scratch((char*)scratch, R, &bs);
+    int ty0, ty1;
+    shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
+    const int gx = tiles_x(a->W), gy = tiles_y(a->H);
+    const int num_tiles = gx * gy;
+
+    if (R > 0) {
+        // the partition ping-pongs A -> B -> A ...: emit into whichever side makes the last
+        // pass land in the persistent (tile_keys, point_list) pair
+        const int tile_bits = num_bits((uint32_t)num_tiles);
+        const bool even = (radix_num_passes(0, tile_bits) % 2) == 0;
+        uint32_t* ka = even ? b.tile_keys : bs.key;
+        uint32_t* va = even ? b.point_list : bs.val;
+        uint32_t* kb = even ? bs.key : b.tile_keys;
+        uint32_t* vb = even ? bs.val : b.point_list;
+        rc = launch_emit_instances(g, a->P, gx, ka, va, s);
+        if (rc) return rc;
+        GSR_STAGE(s, dbg, "emit_instances_kernel");
+        // stable partition by tile id: the depth order inside each tile is preserved
+        rc = radix_sort_pairs(ka, va, kb, vb, R, 0, tile_bits, bs.radix_tmp, s, dbg);
+        if (rc) return rc;
+    }
+    rc = launch_tile_ranges(b.tile_keys, R, im.ranges, num_tiles, s);
+    if (rc) return rc;
+    GSR_STAGE(s, dbg, "tile_ranges_kernel");
+
+    const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
+    rc = launch_render_fwd(*a, g, b, im, colors, ty0, ty1, s);
+    if (rc) return rc;
+    GSR_STAGE(s, dbg, "render_fwd_kernel");
+    return 0;
+}
+
+int gsr_forward(const GsrForwardArgs* a, gsr_alloc_fn alloc, void* ctx, void* stream, int* num_rendered) {
+    int rc = check_fwd_args(a);
+    if (rc) return rc;
+    if (!alloc || !num_rendered) { set_error("alloc / num_rendered is NULL"); return GSR_E_INVALID; }
+    size_t gb = 0, ib = 0, bb = 0, sb = 0;
+    rc = gsr_forward_sizes(a->P, a->M, a->W, a->H, &gb, &ib);
+    if (rc) return rc;
+    void* geom = alloc(ctx, GSR_BUF_GEOM, gb);
+    void* img = alloc(ctx, GSR_BUF_IMG, ib);
+    if (!geom || !img) { set_error("allocation callback returned NULL"); return GSR_E_INVALID; }
+    rc = gsr_forward_geometry(a, geom, img, stream, num_rendered);
+    if (rc) return rc;
+    rc = gsr_binning_sizes(a->P, a->W, a->H, *num_rendered, &bb, &sb);
+    if (rc) return rc;
+    void* bin = alloc(ctx, GSR_BUF_BINNING, bb);
+    void* scr = alloc(ctx, GSR_BUF_SCRATCH, sb);
+    if (!bin || !scr) { set_error("allocation callback returned NULL"); return GSR_E_INVALID; }
+    return gsr_forward_render(a, geom, img, bin, scr, *num_rendered, stream);
+}
+
+int gsr_forward_recolor(const GsrForwardArgs* a, const void* geom_buffer, const void* binning_buffer,
+                        const void* img_buffer, void* img_buffer2, void* stream) {
+    int rc = check_fwd_args(a);
+    if (rc) return rc;
+    if (a->P == 0) return 0;
+    if (!a->colors_precomp) { set_error("gsr_forward_recolor needs colors_precomp"); return GSR_E_INVALID; }
+    if (!geom_buffer || !binning_buffer || !img_buffer || !img_buffer2) { set_error("a buffer is NULL"); return GSR_E_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    GeomState g;
+    ImgState im, im2;
+    BinState b;
+    carve_geom((char*)geom_buffer, a->P, a->M, &g);
+    carve_img((char*)img_buffer, a->W, a->H, &im);
+    carve_img((char*)img_buffer2, a->W, a->H, &im2);
+    // R is only needed for carving offsets inside the binning buffer: point_list is first
+    carve_bin((char*)binning_buffer, 0, &b);
+    int ty0, ty1;
+    shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
+    const size_t T = (size_t)tiles_x(a->W) * tiles_y(a->H);
+    if (im2.ranges != im.ranges)
+        GSR_CUDA(cudaMemcpyAsync(im2.ranges, im.ranges, T * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
+    rc = launch_render_fwd(*a, g, b, im2, a->colors_precomp, ty0, ty1, s);
+    if (rc) return rc;
+    GSR_STAGE(s, a->debug != 0, "render_fwd_kernel(recolor)");
+    return 0;
+}
+
+size_t gsr_backward_scratch_bytes(int P) { return (size_t)(P > 0 ? P : 0) * sizeof(BwdAccum) + 256; }
+
+int gsr_backward(const GsrBackwardArgs* a, void* stream) {
+    if (!a) { set_error("args is NULL"); return GSR_E_INVALID; }
+    if (a->P < 0 || a->W <= 0 || a->H <= 0 || a->R < 0) { set_error("bad sizes"); return GSR_E_INVALID; }
+    if (a->P == 0) return 0;
+    if (!a->means3D || !a->radii || !a->viewmatrix || !a->projmatrix || !a->background || !a->subpixel_offset ||
+        !a->geom_buffer || !a->img_buffer || !a->dL_dpix || !a->accum_scratch || !a->dL_dmean2D || !a->dL_dopacity ||
+        !a->dL_dcolor || !a->dL_dmean3D) { set_error("a required pointer is NULL"); return GSR_E_INVALID; }
+    if (a->R > 0 && !a->binning_buffer) { set_error("binning_buffer is NULL"); return GSR_E_INVALID; }
+    if (a->shs && (!a->dL_dsh || !a->campos || a->M <= 0)) { set_error("shs given but dL_dsh / campos missing"); return GSR_E_INVALID; }
+    if (a->scales && (!a->rotations || !a->dL_dscale || !a->dL_drot)) { set_error("scales given but rotations / dL_dscale / dL_drot missing"); return GSR_E_INVALID; }
+    if (!a->scales && !a->cov3D_precomp) { set_error("neither scales nor cov3D_precomp"); return GSR_E_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool dbg = a->debug != 0;
+    GeomState g;
+    ImgState im;
+    BinState b;
+    carve_geom((char*)a->geom_buffer, a->P, a->M, &g);
+    carve_img((char*)a->img_buffer, a->W, a->H, &im);
+    carve_bin((char*)a->binning_buffer, (size_t)a->R, &b);
+    int ty0, ty1;
+    shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
+
+    char* cur = (char*)a->accum_scratch;
+    BwdAccum* accum;
+    take(cur, accum, (size_t)a->P);
+    GSR_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * sizeof(BwdAccum), s));
+
+    const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
+    int rc = 0;
+    if (a->R > 0) {
+        rc = launch_render_bwd(*a, g, b, im, colors, accum, ty0, ty1, s);
+        if (rc) return rc;
+        GSR_STAGE(s, dbg, "render_bwd_kernel");
+    }
+    rc = launch_preprocess_bwd(*a, g, accum, s);
+    if (rc) return rc;
+    GSR_STAGE(s, dbg, "preprocess_bwd_kernel");
+    return 0;
+}
+
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                     void* stream) {
+    (void)projmatrix;
+    if (P < 0) { set_error("bad P"); return GSR_E_INVALID; }
+    if (P == 0) return 0;
+    if (!means3D || !viewmatrix || !present) { set_error("a required pointer is NULL"); return GSR_E_INVALID; }
+    int rc = launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+    if (rc) return rc;
+    GSR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gsr_img_views(const void* img_buffer, int W, int H, const float** final_T, const uint32_t** n_contrib,
+                  const uint32_t** ranges) {
+    if (!img_buffer) { set_error("img_buffer is NULL"); return GSR_E_INVALID; }
+    ImgState im;
+    carve_img((char*)img_buffer, W, H, &im);
+    if (final_T) *final_T = im.final_T;
+    if (n_contrib) *n_contrib = im.n_contrib;
+    if (ranges) *ranges = reinterpret_cast<const uint32_t*>(im.ranges);
+    return 0;
+}
+
+int gsr_binning_views(const void* binning_buffer, int num_rendered, const uint32_t** point_list) {
+    if (!binning_buffer) { set_error("binning_buffer is NULL"); return GSR_E_INVALID; }
+    BinState b;
+    carve_bin((char*)binning_buffer, (size_t)num_rendered, &b);
+    if (point_list) *point_list = b.point_list;
+    return 0;
+}
+
+int gsr_geom_views(const void* geom_buffer, int P, int M, const float** depths, const float** records,
+                   const uint32_t** tiles_touched, const float** rgb) {
+    if (!geom_buffer) { set_error("geom_buffer is NULL"); return GSR_E_INVALID; }
+    GeomState g;
+    carve_geom((char*)geom_buffer, P, M, &g);
+    if (depths) *depths = g.depths;
+    if (records) *records = reinterpret_cast<const float*>(g.rec);
+    if (tiles_touched) *tiles_touched = g.tiles_touched;
+    if (rgb) *rgb = g.rgb;
+    return 0;
+}
+
+int gsr_get_stats(const void* geom_buffer, int P, int M, void* stream, GsrStats* out) {
+    if (!geom_buffer || !out) { set_error("NULL argument"); return GSR_E_INVALID; }
+    GeomState g;
+    carve_geom((char*)geom_buffer, P, M, &g);
+    int32_t c[8];
+    cudaStream_t s = (cudaStream_t)stream;
+    GSR_CUDA(cudaMemcpyAsync(c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA(cudaStreamSynchronize(s));
+    out->num_visible = c[1];
+    out->num_rendered = c[2];
+    out->num_tiles = 0;
+    out->reserved = 0;
+    return 0;
+}
+
+}  // extern "C"
+
+namespace gsr {
+
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                                           const float* __restrict__ view, uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+    const float vz = view[2] * x + view[6] * y + view[10] * z + view[14];
+    present[idx] = vz <= NEAR_Z ? 0 : 1;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+    return 0;
+}
+
+}  // namespace gsr

@@ -1,0 +1,117 @@
+// common.cuh -- shared declarations of libgsrast (sm_100a Gaussian-splat rasterizer).
+// Internal header: the public boundary is include/gsrast.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "gsrast.h"
+
+namespace gsr {
+
+constexpr int TILE = 16;              // tile edge in pixels (reference config.h:16-17)
+constexpr int TILE_PIX = TILE * TILE;
+constexpr float NEAR_Z = 0.2f;        // near cull (reference auxiliary.h:154)
+
+// ----------------------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define GSR_CUDA(expr)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return gsr::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// launch check; with debug also synchronises the stream (reference CHECK_CUDA, auxiliary.h:166-173)
+#define GSR_STAGE(stream, debug, name)                                        \
+    do {                                                                      \
+        cudaError_t _e = cudaGetLastError();                                  \
+        if (_e == cudaSuccess && (debug)) _e = cudaStreamSynchronize(stream); \
+        if (_e != cudaSuccess) return gsr::cuda_fail(_e, name, __FILE__, __LINE__); \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------
+// buffer layouts (carved out of the caller's opaque byte buffers)
+// ----------------------------------------------------------------------------------------
+struct TileRect { uint16_t x0, y0, x1, y1; };   // half-open tile rectangle of one Gaussian
+
+struct GeomState {
+    // persistent (read by the backward pass)
+    float4*   rec;            // [2P] {x, y, conic.x, conic.y | conic.z, opacity*coef, depth, 0}
+    float*    rgb;            // [3P] SH-evaluated colours (SH path only)
+    uint8_t*  clamped;        // [P]  bit c set: channel c was clamped to 0 (SH path only)
+    float*    depths;         // [P]  view-space z (exported for parity tests)
+    uint32_t* tiles_touched;  // [P]
+    TileRect* rect;           // [P]
+    int32_t*  counters;       // [8]  0: prefiltered violation, 1: visible count, 2: R
+    // transient (depth ordering + instance offsets)
+    uint32_t* key_a;          // [P]
+    uint32_t* key_b;          // [P]
+    uint32_t* val_a;          // [P]
+    uint32_t* val_b;          // [P]
+    uint32_t* order;          // alias of val_a: after the 4-pass depth sort, Gaussian ids front to back
+    uint32_t* offsets;        // [P+1] exclusive scan of tiles_touched in depth order
+    uint32_t* radix_tmp;      // histogram / scan temporaries
+    size_t    radix_tmp_count;
+};
+
+struct ImgState {
+    float*    final_T;        // [N]  first, 128-B aligned (reference ImageState order)
+    uint32_t* n_contrib;      // [N]
+    uint2*    ranges;         // [T]
+};
+
+struct BinState {
+    uint32_t* point_list;     // [R] sorted Gaussian ids (tile-major, depth-minor)
+    uint32_t* tile_keys;      // [R] sorted tile ids
+};
+
+struct BinScratch {
+    uint32_t* key;            // [R]
+    uint32_t* val;            // [R]
+    uint32_t* radix_tmp;
+    size_t    radix_tmp_count;
+};
+
+size_t carve_geom(char* base, int P, int M, GeomState* out);       // returns bytes used
+size_t carve_img(char* base, int W, int H, ImgState* out);
+size_t carve_bin(char* base, size_t R, BinState* out);
+size_t carve_bin_scratch(char* base, size_t R, BinScratch* out);
+
+inline int tiles_x(int W) { return (W + TILE - 1) / TILE; }
+inline int tiles_y(int H) { return (H + TILE - 1) / TILE; }
+
+// ----------------------------------------------------------------------------------------
+// stage launchers (each enqueues on `stream`, returns 0 or a status code)
+// ----------------------------------------------------------------------------------------
+int launch_preprocess_fwd(const GsrForwardArgs& a, const GeomState& g, int ty0, int ty1, cudaStream_t s);
+
+// stable LSD radix partition of (key,val) pairs on key bits [shift, shift+bits)
+size_t radix_tmp_elems(size_t n);
+int radix_num_passes(int begin_bit, int end_bit);
+// input in (key_a,val_a); result in A if radix_num_passes() is even, else in B; both clobbered
+int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, size_t n,
+                     int begin_bit, int end_bit, uint32_t* tmp, cudaStream_t s, bool debug);
+// exclusive scan of gathered counts: out[i] = sum_{j<i} counts[perm[j]], out[n] = total
+int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, size_t n,
+                  uint32_t* tmp, cudaStream_t s);
+size_t scan_tmp_elems(size_t n);
+
+int launch_emit_instances(const GeomState& g, int P, int gx, uint32_t* keys, uint32_t* vals, cudaStream_t s);
+int launch_tile_ranges(const uint32_t* sorted_tile_keys, size_t R, uint2* ranges, int num_tiles, cudaStream_t s);
+
+int launch_render_fwd(const GsrForwardArgs& a, const GeomState& g, const BinState& b, const ImgState& im,
+                      const float* colors, int ty0, int ty1, cudaStream_t s);
+
+struct BwdAccum { float4 a, b, c; };  // per-Gaussian packed partial gradients (48 B)
+// a = {dmean2D.x, dmean2D.y, |dmean2D|, dconic.x}  b = {dconic.y, dconic.w, dopacity, dcolor.r}
+// c = {dcolor.g, dcolor.b, -, -}
+int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinState& b, const ImgState& im,
+                      const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s);
+int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, const BwdAccum* accum, cudaStream_t s);
+
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
+
+}  // namespace gsr

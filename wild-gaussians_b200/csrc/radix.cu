@@ -1,0 +1,336 @@
+// radix.cu -- stable LSD radix partition of (u32 key, u32 value) pairs and an exclusive scan
+// of gathered counts.  Hand-written replacement for the two CUB calls on the reference's
+// path (cub::DeviceRadixSort::SortPairs, rasterizer_impl.cu:303-311, and
+// cub::DeviceScan::InclusiveSum, :280).
+//
+// Why the result equals the reference's: both are stable sorts of the same multiset, and a
+// stable sort has exactly one result.  The reference sorts R 64-bit keys (tile | depth) in
+// one go; here the P Gaussians are ordered by depth bits once (4 passes over P pairs) and
+// the R instances, emitted in that depth order, are then stably partitioned by their tile
+// id only (2 passes over R pairs) -- see binning.cu.
+//
+// One pass = three launches, no spin-waiting between CTAs (so nothing can dead-lock):
+//   radix_hist_kernel    per-CTA digit histogram of a CHUNK of the input   -> hist[digit][cta]
+//   radix_rowscan_kernel one CTA per digit: exclusive scan along the row    -> hist (in place), total[digit]
+//   radix_scatter_kernel re-reads the chunk, ranks every item among equal digits in
+//                        (warp, round, lane) = input order with match.any, and scatters
+// All traffic is coalesced on the read side; writes are digit-run coalesced.
+#include "common.cuh"
+
+namespace gsr {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;                       // items per thread
+constexpr int RS_CHUNK = RS_THREADS * RS_ITEMS;    // items per CTA
+constexpr int RS_WARP_ITEMS = 32 * RS_ITEMS;       // items per warp (contiguous in the input)
+
+static inline size_t radix_ctas(size_t n) { return (n + RS_CHUNK - 1) / RS_CHUNK; }
+
+size_t radix_tmp_elems(size_t n) {
+    // hist[RADIX][ctas] + total[RADIX]
+    return (size_t)RADIX * radix_ctas(n) + RADIX + 64;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int shift,
+                                                                uint32_t mask, uint32_t* __restrict__ hist, uint32_t ctas) {
+    __shared__ uint32_t s_hist[RADIX];
+    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * RS_CHUNK;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 4
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const size_t i = base + (size_t)warp * RS_WARP_ITEMS + r * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((keys[i] >> shift) & mask) : (RADIX + lane);
+        // warp-aggregated histogram update: neighbouring items often share a digit
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        if (valid && lane == (__ffs(peers) - 1)) atomicAdd(&s_hist[d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) hist[(size_t)i * ctas + blockIdx.x] = s_hist[i];
+}
+
+// one CTA per digit; exclusive scan of hist[digit][0..ctas) in place, row total -> total[digit]
+__global__ void __launch_bounds__(1024) radix_rowscan_kernel(uint32_t* __restrict__ hist, uint32_t ctas,
+                                                             uint32_t* __restrict__ total) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    uint32_t* row = hist + (size_t)blockIdx.x * ctas;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ctas; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < ctas ? row[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t warp_excl = warp == 0 ? 0u : s_warp[warp - 1];
+        const uint32_t carry = s_carry;
+        if (i < ctas) row[i] = carry + warp_excl + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
+}
+
+template <bool WRITE_KEYS>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                   const uint32_t* __restrict__ vals_in,
+                                                                   uint32_t* __restrict__ keys_out,
+                                                                   uint32_t* __restrict__ vals_out, size_t n, int shift,
+                                                                   uint32_t mask, const uint32_t* __restrict__ hist,
+                                                                   const uint32_t* __restrict__ total, uint32_t ctas) {
+    __shared__ uint32_t s_cnt[RS_WARPS][RADIX];   // per-warp digit counters, later global bases
+    __shared__ uint32_t s_digit_base[RADIX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
+
+    // exclusive scan of the digit totals (256 values, one per thread)
+    {
+        __shared__ uint32_t s_w[RS_WARPS];
+        const uint32_t v = total[threadIdx.x];
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        uint32_t off = 0;
+        for (int w = 0; w < warp; ++w) off += s_w[w];
+        s_digit_base[threadIdx.x] = off + x - v + hist[(size_t)threadIdx.x * ctas + blockIdx.x];
+    }
+    __syncthreads();
+
+    const size_t base = (size_t)blockIdx.x * RS_CHUNK + (size_t)warp * RS_WARP_ITEMS;
+    uint32_t key[RS_ITEMS], val[RS_ITEMS];
+    uint16_t rank[RS_ITEMS];
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const size_t i = base + r * 32 + lane;
+        const bool valid = i < n;
+        key[r] = valid ? keys_in[i] : 0u;
+        val[r] = valid ? vals_in[i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const size_t i = base + r * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((key[r] >> shift) & mask) : (RADIX + lane);
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        uint32_t old = 0;
+        if (valid) old = s_cnt[warp][d];
+        __syncwarp();
+        if (valid && lane == (__ffs(peers) - 1)) s_cnt[warp][d] = old + __popc(peers);
+        __syncwarp();
+        rank[r] = (uint16_t)(old + __popc(peers & lt_mask));
+    }
+    __syncthreads();
+    // per digit: running offset over warps + global base of this CTA -> s_cnt becomes the
+    // absolute output position of the first item of (warp, digit)
+    {
+        const int d = threadIdx.x;
+        uint32_t run = s_digit_base[d];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t c = s_cnt[w][d];
+            s_cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const size_t i = base + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (key[r] >> shift) & mask;
+            const uint32_t pos = s_cnt[warp][d] + rank[r];
+            if (WRITE_KEYS) keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+int radix_num_passes(int begin_bit, int end_bit) {
+    const int nbits = end_bit - begin_bit;
+    return nbits <= 0 ? 0 : (nbits + RADIX_BITS - 1) / RADIX_BITS;
+}
+
+int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, size_t n, int begin_bit,
+                     int end_bit, uint32_t* tmp, cudaStream_t s, bool debug) {
+    // Stable sort on key bits [begin_bit, end_bit).  The input is (key_a, val_a); passes
+    // ping-pong A -> B -> A ..., clobbering both.  With an even number of passes
+    // (radix_num_passes) the result is in A, with an odd number in B; callers place their
+    // buffers accordingly.
+    if (n == 0) return 0;
+    const int passes = radix_num_passes(begin_bit, end_bit);
+    const uint32_t ctas = (uint32_t)radix_ctas(n);
+    uint32_t* hist = tmp;
+    uint32_t* total = tmp + (size_t)RADIX * ctas;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = begin_bit + pass * RADIX_BITS;
+        const int bits = min(RADIX_BITS, end_bit - shift);
+        const uint32_t mask = (1u << bits) - 1u;
+        const bool a_to_b = (pass % 2) == 0;
+        const uint32_t* kin = a_to_b ? key_a : key_b;
+        const uint32_t* vin = a_to_b ? val_a : val_b;
+        uint32_t* kout = a_to_b ? key_b : key_a;
+        uint32_t* vout = a_to_b ? val_b : val_a;
+        radix_hist_kernel<<<ctas, RS_THREADS, 0, s>>>(kin, n, shift, mask, hist, ctas);
+        GSR_STAGE(s, debug, "radix_hist_kernel");
+        radix_rowscan_kernel<<<RADIX, 1024, 0, s>>>(hist, ctas, total);
+        GSR_STAGE(s, debug, "radix_rowscan_kernel");
+        radix_scatter_kernel<true><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, total, ctas);
+        GSR_STAGE(s, debug, "radix_scatter_kernel");
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------
+// exclusive scan of counts gathered through a permutation (instance offsets in depth order)
+// ----------------------------------------------------------------------------------------
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_CHUNK = SC_THREADS * SC_ITEMS;
+
+size_t scan_tmp_elems(size_t n) { return (n + SC_CHUNK - 1) / SC_CHUNK + 64; }
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp, uint32_t* block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SC_THREADS / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) off += c;
+        tot += c;
+    }
+    *block_total = tot;
+    __syncthreads();
+    return off + x - v;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ counts,
+                                                                 const uint32_t* __restrict__ perm, size_t n,
+                                                                 uint32_t* __restrict__ partial) {
+    __shared__ uint32_t s_warp[SC_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * SC_CHUNK;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const size_t i = base + (size_t)k * SC_THREADS + threadIdx.x;
+        if (i < n) sum += counts[perm ? perm[i] : i];
+    }
+    uint32_t tot;
+    block_exclusive_scan_256(sum, s_warp, &tot);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+// single CTA: exclusive scan of the partials in place, grand total -> partial[m]
+__global__ void __launch_bounds__(1024) scan_partials_kernel(uint32_t* __restrict__ partial, uint32_t m) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < m; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < m ? partial[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t warp_excl = warp == 0 ? 0u : s_warp[warp - 1];
+        const uint32_t carry = s_carry;
+        if (i < m) partial[i] = carry + warp_excl + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[m] = s_carry;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) scan_apply_kernel(const uint32_t* __restrict__ counts,
+                                                                const uint32_t* __restrict__ perm, size_t n,
+                                                                const uint32_t* __restrict__ partial, uint32_t m,
+                                                                uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_warp[SC_THREADS / 32];
+    // blocked arrangement: thread t owns items [t*SC_ITEMS, (t+1)*SC_ITEMS) of the chunk
+    const size_t base = (size_t)blockIdx.x * SC_CHUNK + (size_t)threadIdx.x * SC_ITEMS;
+    uint32_t v[SC_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const size_t i = base + k;
+        v[k] = i < n ? counts[perm ? perm[i] : i] : 0u;
+        sum += v[k];
+    }
+    uint32_t tot;
+    uint32_t off = block_exclusive_scan_256(sum, s_warp, &tot) + partial[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const size_t i = base + k;
+        if (i < n) out[i] = off;
+        off += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = partial[m];
+}
+
+int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, size_t n, uint32_t* tmp, cudaStream_t s) {
+    if (n == 0) {
+        GSR_CUDA(cudaMemsetAsync(out, 0, 4, s));
+        return 0;
+    }
+    const uint32_t m = (uint32_t)((n + SC_CHUNK - 1) / SC_CHUNK);
+    scan_reduce_kernel<<<m, SC_THREADS, 0, s>>>(counts, perm, n, tmp);
+    scan_partials_kernel<<<1, 1024, 0, s>>>(tmp, m);
+    scan_apply_kernel<<<m, SC_THREADS, 0, s>>>(counts, perm, n, tmp, m, out);
+    GSR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gsr

@@ -1,0 +1,298 @@
+"""``diff_gaussian_rasterization._C`` -- host-side binding of ``libgsrast.so``.
+
+Mirrors the three functions the reference's pybind11 module exports
+(``submodules/diff-gaussian-rasterization/ext.cpp:15-19``), same positional arguments, same
+returned tuples (``rasterize_points.cu:35-119,121-204,206-225``), but implemented as a thin
+ctypes shim over the C ABI in ``include/gsrast.h``: torch is used only to allocate device
+memory and to name the current stream.  There is no CPU fallback -- if the CUDA library is
+missing the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libgsrast.so"))
+
+NUM_CHANNELS = 3
+
+
+class GsrForwardArgs(Structure):
+    _fields_ = [
+        ("P", c_int), ("D", c_int), ("M", c_int), ("W", c_int), ("H", c_int),
+        ("background", c_void_p), ("means3D", c_void_p), ("shs", c_void_p), ("colors_precomp", c_void_p),
+        ("opacities", c_void_p), ("scales", c_void_p), ("scale_modifier", c_float), ("rotations", c_void_p),
+        ("cov3D_precomp", c_void_p), ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p),
+        ("tan_fovx", c_float), ("tan_fovy", c_float), ("kernel_size", c_float), ("subpixel_offset", c_void_p),
+        ("prefiltered", c_int), ("debug", c_int), ("tile_y0", c_int), ("tile_y1", c_int),
+        ("out_color", c_void_p), ("radii", c_void_p),
+    ]
+
+
+class GsrBackwardArgs(Structure):
+    _fields_ = [
+        ("P", c_int), ("D", c_int), ("M", c_int), ("R", c_int), ("W", c_int), ("H", c_int),
+        ("background", c_void_p), ("means3D", c_void_p), ("shs", c_void_p), ("colors_precomp", c_void_p),
+        ("scales", c_void_p), ("scale_modifier", c_float), ("rotations", c_void_p), ("cov3D_precomp", c_void_p),
+        ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p),
+        ("tan_fovx", c_float), ("tan_fovy", c_float), ("kernel_size", c_float), ("subpixel_offset", c_void_p),
+        ("radii", c_void_p), ("geom_buffer", c_void_p), ("binning_buffer", c_void_p), ("img_buffer", c_void_p),
+        ("dL_dpix", c_void_p), ("debug", c_int), ("tile_y0", c_int), ("tile_y1", c_int),
+        ("accum_scratch", c_void_p),
+        ("dL_dmean2D", c_void_p), ("dL_dconic", c_void_p), ("dL_dopacity", c_void_p), ("dL_dcolor", c_void_p),
+        ("dL_dmean3D", c_void_p), ("dL_dcov3D", c_void_p), ("dL_dsh", c_void_p), ("dL_dscale", c_void_p),
+        ("dL_drot", c_void_p),
+    ]
+
+
+class GsrStats(Structure):
+    _fields_ = [("num_rendered", c_int), ("num_visible", c_int), ("num_tiles", c_int), ("reserved", c_int)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is deliberately no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.gsr_abi_version.restype = c_int
+    lib.gsr_last_error.restype = c_char_p
+    lib.gsr_forward_sizes.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]
+    lib.gsr_forward_geometry.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, POINTER(c_int)]
+    lib.gsr_binning_sizes.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]
+    lib.gsr_forward_render.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    lib.gsr_forward_recolor.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.gsr_backward_scratch_bytes.argtypes = [c_int]
+    lib.gsr_backward_scratch_bytes.restype = c_size_t
+    lib.gsr_backward.argtypes = [POINTER(GsrBackwardArgs), c_void_p]
+    lib.gsr_mark_visible.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.gsr_img_views.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
+    lib.gsr_binning_views.argtypes = [c_void_p, c_int, POINTER(c_void_p)]
+    lib.gsr_geom_views.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
+    lib.gsr_get_stats.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(GsrStats)]
+    for name in ("gsr_forward_sizes", "gsr_forward_geometry", "gsr_binning_sizes", "gsr_forward_render",
+                 "gsr_forward_recolor", "gsr_backward", "gsr_mark_visible", "gsr_img_views", "gsr_binning_views",
+                 "gsr_geom_views", "gsr_get_stats"):
+        getattr(lib, name).restype = c_int
+    if lib.gsr_abi_version() != 1:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.gsr_abi_version()} != 1")
+    return lib
+
+
+_lib = _load()
+
+# Tile-row shard used by the calls below (multi-GPU partition, see parallel.py); (0, 0) = whole image.
+_shard = (0, 0)
+
+
+def set_tile_row_shard(y0: int, y1: int) -> None:
+    global _shard
+    _shard = (int(y0), int(y1))
+
+
+def get_tile_row_shard():
+    return _shard
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = _lib.gsr_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def _ptr(t: torch.Tensor | None):
+    """Device pointer of a tensor, NULL for the reference's "absent" zero-element tensors
+    (``__init__.py:218-228``: empty CPU tensors stand for None)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, device) -> torch.Tensor:
+    if t.numel() == 0:
+        return t
+    if t.device != device or t.dtype != torch.float32:
+        t = t.to(device=device, dtype=torch.float32)
+    return t.contiguous()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset, image_height,
+                        image_width, sh, degree, campos, prefiltered, debug):
+    """Drop-in for ``RasterizeGaussiansCUDA`` (rasterize_points.cu:35-119).
+
+    Returns ``(num_rendered, out_color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer)``.
+    """
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("diff_gaussian_rasterization (sm_100a build) needs CUDA tensors; there is no CPU path")
+    dev = means3D.device
+    P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+    with torch.cuda.device(dev):
+        out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+        radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+        byte = dict(dtype=torch.uint8, device=dev)
+        if P == 0:
+            e = torch.empty((0,), **byte)
+            return 0, out_color, radii, e, e.clone(), e.clone()
+        M = int(sh.size(1)) if sh.numel() != 0 else 0
+
+        keep = [_f32c(t, dev) for t in (background, means3D, colors, opacity, scales, rotations, cov3D_precomp,
+                                        viewmatrix, projmatrix, subpixel_offset, sh, campos)]
+        (background, means3D, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
+         subpixel_offset, sh, campos) = keep
+
+        a = GsrForwardArgs()
+        a.P, a.D, a.M, a.W, a.H = P, int(degree), M, W, H
+        a.background = _ptr(background); a.means3D = _ptr(means3D); a.shs = _ptr(sh)
+        a.colors_precomp = _ptr(colors); a.opacities = _ptr(opacity); a.scales = _ptr(scales)
+        a.scale_modifier = float(scale_modifier); a.rotations = _ptr(rotations)
+        a.cov3D_precomp = _ptr(cov3D_precomp); a.viewmatrix = _ptr(viewmatrix); a.projmatrix = _ptr(projmatrix)
+        a.campos = _ptr(campos); a.tan_fovx = float(tan_fovx); a.tan_fovy = float(tan_fovy)
+        a.kernel_size = float(kernel_size); a.subpixel_offset = _ptr(subpixel_offset)
+        a.prefiltered = int(bool(prefiltered)); a.debug = int(bool(debug))
+        a.tile_y0, a.tile_y1 = _shard
+        a.out_color = out_color.data_ptr(); a.radii = radii.data_ptr()
+
+        gb, ib = c_size_t(0), c_size_t(0)
+        _check(_lib.gsr_forward_sizes(P, M, W, H, byref(gb), byref(ib)), "gsr_forward_sizes")
+        geom = torch.empty((gb.value,), **byte)
+        img = torch.empty((ib.value,), **byte)
+        stream = _stream(dev)
+        R = c_int(0)
+        _check(_lib.gsr_forward_geometry(byref(a), geom.data_ptr(), img.data_ptr(), stream, byref(R)),
+               "gsr_forward_geometry")
+        bb, sb = c_size_t(0), c_size_t(0)
+        _check(_lib.gsr_binning_sizes(P, W, H, R.value, byref(bb), byref(sb)), "gsr_binning_sizes")
+        binning = torch.empty((bb.value,), **byte)
+        scratch = torch.empty((sb.value,), **byte)
+        _check(_lib.gsr_forward_render(byref(a), geom.data_ptr(), img.data_ptr(), binning.data_ptr(),
+                                       scratch.data_ptr(), R.value, stream), "gsr_forward_render")
+        # `scratch` goes back to torch's stream-ordered caching allocator here: any later
+        # allocation on this stream is ordered after the kernels that use it.
+        del scratch
+    return R.value, out_color, radii, geom, binning, img
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size,
+                                 subpixel_offset, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                 imageBuffer, debug):
+    """Drop-in for ``RasterizeGaussiansBackwardCUDA`` (rasterize_points.cu:121-204).
+
+    Returns ``(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)``.
+    """
+    dev = means3D.device
+    P = int(means3D.size(0))
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    M = int(sh.size(1)) if sh.numel() != 0 else 0
+    with torch.cuda.device(dev):
+        f32 = dict(dtype=torch.float32, device=dev)
+        # every row of every output is written by the kernel: empty, not zeros
+        alloc = torch.empty if P > 0 else torch.zeros
+        dL_dmeans3D = alloc((P, 3), **f32)
+        dL_dmeans2D = alloc((P, 3), **f32)
+        dL_dcolors = alloc((P, NUM_CHANNELS), **f32)
+        dL_dopacity = alloc((P, 1), **f32)
+        dL_dcov3D = alloc((P, 6), **f32)
+        dL_dsh = alloc((P, M, 3), **f32)
+        have_scales = scales.numel() != 0
+        dL_dscales = alloc((P, 3), **f32) if have_scales else torch.zeros((P, 3), **f32)
+        dL_drotations = alloc((P, 4), **f32) if have_scales else torch.zeros((P, 4), **f32)
+        if P == 0:
+            return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+
+        keep = [_f32c(t, dev) for t in (background, means3D, colors, scales, rotations, cov3D_precomp, viewmatrix,
+                                        projmatrix, subpixel_offset, dL_dout_color, sh, campos)]
+        (background, means3D, colors, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, subpixel_offset,
+         dL_dout_color, sh, campos) = keep
+        radii = radii.contiguous()
+        scratch = torch.empty((_lib.gsr_backward_scratch_bytes(P),), dtype=torch.uint8, device=dev)
+
+        a = GsrBackwardArgs()
+        a.P, a.D, a.M, a.R, a.W, a.H = P, int(degree), M, int(R), W, H
+        a.background = _ptr(background); a.means3D = _ptr(means3D); a.shs = _ptr(sh)
+        a.colors_precomp = _ptr(colors); a.scales = _ptr(scales); a.scale_modifier = float(scale_modifier)
+        a.rotations = _ptr(rotations); a.cov3D_precomp = _ptr(cov3D_precomp)
+        a.viewmatrix = _ptr(viewmatrix); a.projmatrix = _ptr(projmatrix); a.campos = _ptr(campos)
+        a.tan_fovx = float(tan_fovx); a.tan_fovy = float(tan_fovy); a.kernel_size = float(kernel_size)
+        a.subpixel_offset = _ptr(subpixel_offset); a.radii = radii.data_ptr()
+        a.geom_buffer = _ptr(geomBuffer); a.binning_buffer = _ptr(binningBuffer); a.img_buffer = _ptr(imageBuffer)
+        a.dL_dpix = _ptr(dL_dout_color); a.debug = int(bool(debug))
+        a.tile_y0, a.tile_y1 = _shard
+        a.accum_scratch = scratch.data_ptr()
+        a.dL_dmean2D = dL_dmeans2D.data_ptr(); a.dL_dconic = None
+        a.dL_dopacity = dL_dopacity.data_ptr(); a.dL_dcolor = dL_dcolors.data_ptr()
+        a.dL_dmean3D = dL_dmeans3D.data_ptr(); a.dL_dcov3D = dL_dcov3D.data_ptr()
+        a.dL_dsh = _ptr(dL_dsh)
+        a.dL_dscale = dL_dscales.data_ptr() if have_scales else None
+        a.dL_drot = dL_drotations.data_ptr() if have_scales else None
+        _check(_lib.gsr_backward(byref(a), _stream(dev)), "gsr_backward")
+        del scratch
+    return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    """Drop-in for ``markVisible`` (rasterize_points.cu:206-225): bool[P], view-space z > 0.2."""
+    if not means3D.is_cuda:
+        raise RuntimeError("diff_gaussian_rasterization (sm_100a build) needs CUDA tensors; there is no CPU path")
+    dev = means3D.device
+    P = int(means3D.size(0))
+    with torch.cuda.device(dev):
+        present = torch.zeros((P,), dtype=torch.bool, device=dev)
+        if P != 0:
+            m = _f32c(means3D, dev)
+            v = _f32c(viewmatrix, dev)
+            pm = _f32c(projmatrix, dev)
+            _check(_lib.gsr_mark_visible(P, m.data_ptr(), v.data_ptr(), pm.data_ptr(), present.data_ptr(),
+                                         _stream(dev)), "gsr_mark_visible")
+    return present
+
+
+# ---- extras (not part of the reference surface; used by parity tests and the benchmark) ----------
+
+def _as_tensor(ptr: int, nbytes: int, owner: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """View of `nbytes` bytes at device address `ptr` inside `owner` (a uint8 buffer)."""
+    off = ptr - owner.data_ptr()
+    assert 0 <= off and off + nbytes <= owner.numel(), "view outside its buffer"
+    return owner[off:off + nbytes].view(dtype)
+
+
+def debug_views(geomBuffer, binningBuffer, imgBuffer, P, M, W, H, R):
+    """Expose the integer artefacts the parity tests compare bit-exactly."""
+    out = {}
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    ft, nc, rg = c_void_p(), c_void_p(), c_void_p()
+    _check(_lib.gsr_img_views(imgBuffer.data_ptr(), W, H, byref(ft), byref(nc), byref(rg)), "gsr_img_views")
+    out["final_T"] = _as_tensor(ft.value, 4 * W * H, imgBuffer, torch.float32).view(H, W)
+    out["n_contrib"] = _as_tensor(nc.value, 4 * W * H, imgBuffer, torch.int32).view(H, W)
+    out["ranges"] = _as_tensor(rg.value, 8 * T, imgBuffer, torch.int32).view(T, 2)
+    if R > 0:
+        pl = c_void_p()
+        _check(_lib.gsr_binning_views(binningBuffer.data_ptr(), R, byref(pl)), "gsr_binning_views")
+        out["point_list"] = _as_tensor(pl.value, 4 * R, binningBuffer, torch.int32)
+    else:
+        out["point_list"] = torch.empty((0,), dtype=torch.int32, device=imgBuffer.device)
+    d, rec, tt, rgb = c_void_p(), c_void_p(), c_void_p(), c_void_p()
+    _check(_lib.gsr_geom_views(geomBuffer.data_ptr(), P, M, byref(d), byref(rec), byref(tt), byref(rgb)), "gsr_geom_views")
+    out["depths"] = _as_tensor(d.value, 4 * P, geomBuffer, torch.float32)
+    out["records"] = _as_tensor(rec.value, 32 * P, geomBuffer, torch.float32).view(P, 8)
+    out["tiles_touched"] = _as_tensor(tt.value, 4 * P, geomBuffer, torch.int32)
+    if M > 0:
+        out["rgb"] = _as_tensor(rgb.value, 12 * P, geomBuffer, torch.float32).view(P, 3)
+    return out
+
+
+def stats(geomBuffer, P, M):
+    s = GsrStats()
+    _check(_lib.gsr_get_stats(geomBuffer.data_ptr(), P, M, _stream(geomBuffer.device), byref(s)), "gsr_get_stats")
+    return {"num_rendered": s.num_rendered, "num_visible": s.num_visible}
