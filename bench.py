@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward rasterization throughput on synthetic Gaussian clouds (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One *step* = one forward + one backward rasterization of the named workload (default C3: 3M Gaussians,
+1920x1080, colours precomputed -- the path wildgaussians/method.py uses).  Inputs are synthetic
+(seeded generator, wild-gaussians_b200/synthetic.py) and resident in HBM when the timed region starts.
+Rank 0 prints ONE JSON line:
+
+  value / ms_per_step   Gaussians*pixels/s = P*N / t_step, device-timed (CUDA events), max over ranks
+  e2e                   the same metric through the public Python API (GaussianRasterizer + autograd) with every
+                        tensor argument copied from pinned host memory each step and the image + all gradients read
+                        back to the host, copies inside the timed region
+  roofline              dominant kernel: algorithmic bytes / its event-timed duration vs MEASURED_PEAKS.json
+  roofline_path         SURVEY.md 8(d) whole-path formula (B_fwd + B_bwd) / (t_fwd + t_bwd)
+  stages                per-stage device times (events inside libgsrast, averaged over K profiled steps run right
+                        after the timed region) and their algorithmic bytes
+  cpu_baseline          the CPU oracle (oracle/oracle.c, OpenMP) on a bounded sample of the workload, rank 0, N=1
+
+--impl reference times the UNMODIFIED reference rasterizer compiled for sm_100a (oracle/_ref/libdgr_ref.so; the
+reference has no CPU implementation of this path, its own implementation IS CUDA) on the same tensors; if that
+library did not travel with the snapshot it falls back to the CPU oracle port.  Rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "wild-gaussians_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+import synthetic  # noqa: E402
+
+FALLBACK_HBM_GBS = 6650.0
+
+
+# ----------------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed regions."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.rows, self.proc, self.th = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.th = threading.Thread(target=pump, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def call_args(d):
+    e = torch.Tensor([])
+    return (d["bg"], d["means3D"], d.get("colors_precomp", e), d["opacities"], d.get("scales", e),
+            d.get("rotations", e), d["scale_modifier"], d.get("cov3D_precomp", e), d["viewmatrix"], d["projmatrix"],
+            d["tanfovx"], d["tanfovy"], d["kernel_size"], d["subpixel_offset"], d["image_height"], d["image_width"],
+            d.get("shs", e), d["sh_degree"], d["campos"], False, False)
+
+
+def backward_args(d, radii, geom, R, binning, img):
+    e = torch.Tensor([])
+    return (d["bg"], d["means3D"], radii, d.get("colors_precomp", e), d.get("scales", e), d.get("rotations", e),
+            d["scale_modifier"], d.get("cov3D_precomp", e), d["viewmatrix"], d["projmatrix"], d["tanfovx"],
+            d["tanfovy"], d["kernel_size"], d["subpixel_offset"], d["dL_dpix"], d.get("shs", e), d["sh_degree"],
+            d["campos"], geom, R, binning, img, False)
+
+
+def path_bytes(P, V, R, N, sh_M):
+    """algorithmic (compulsory) bytes of one forward and one backward."""
+    A_in = 44 + (12 if sh_M == 0 else 12 * sh_M)
+    A_g = 56 + (12 if sh_M == 0 else 12 * sh_M)
+    B_fwd = P * (A_in + 4) + V * 40 + R * 8 + R * 36 + N * 28
+    B_bwd = R * 40 + N * 28 + V * 40 + P * (A_in + A_g)
+    return B_fwd, B_bwd
+
+
+def stage_bytes(P, V, R, N, T, sh_M, visited):
+    """Algorithmic bytes per stage (DESIGN.md "kernels" table).  `visited` = sum over tiles of the instances the
+    composite actually walks (<= R; the rest of each tile's list is occluded and never read)."""
+    col = 12 if sh_M == 0 else 12 * sh_M
+    return {
+        "preprocess_fwd": P * (44 + (0 if sh_M == 0 else col) + 4 + 4 + 8 + 8) + V * (32 + 4),
+        "depth_sort": P * 8 * 2,                 # one read + one write of the (key, id) pairs
+        "offset_scan": P * (4 + 4 + 4),
+        "emit_instances": P * (4 + 8 + 4) + R * 8,
+        "tile_sort": R * 8 * 2,                  # one read + one write of the (tile, id) pairs
+        "tile_ranges": R * 4 + T * 8,
+        "render_fwd": visited * (4 + 32 + 12) + N * (8 + 12 + 4 + 4) + T * 8,
+        "render_bwd": visited * (4 + 32 + 12 + 48) + N * (8 + 12 + 4 + 4) + T * 8,
+        "preprocess_bwd": P * (4 + 44 + 56 + 12) + V * (48 + 32),
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------
+# arms
+# ----------------------------------------------------------------------------------------------------------
+def time_steps(step, steps, warmup, dev, world):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps
+
+
+def make_e2e_step(mod_api, scene, dev, settings_cls, sharded=None):
+    """Public-API step with host buffers: H2D of every tensor argument from pinned memory, forward, backward,
+    D2H of the image and of every gradient into pinned memory."""
+    keys = [k for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp", "shs", "bg", "viewmatrix",
+                        "projmatrix", "campos", "subpixel_offset", "dL_dpix") if k in scene]
+    host = {k: scene[k].contiguous().pin_memory() for k in keys}
+    leaves_k = [k for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp", "shs") if k in scene]
+    H, W, P = scene["image_height"], scene["image_width"], scene["means3D"].shape[0]
+    out_host = {"image": torch.empty((3, H, W)).pin_memory(), "means2D": torch.empty((P, 3)).pin_memory()}
+    for k in leaves_k:
+        out_host[k] = torch.empty_like(scene[k]).pin_memory()
+    h2d = sum(v.numel() * 4 for v in host.values())
+    d2h = sum(v.numel() * 4 for v in out_host.values())
+
+    def step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        st = settings_cls(image_height=H, image_width=W, tanfovx=scene["tanfovx"], tanfovy=scene["tanfovy"],
+                          kernel_size=scene["kernel_size"], subpixel_offset=d["subpixel_offset"], bg=d["bg"],
+                          scale_modifier=1.0, viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"],
+                          sh_degree=scene["sh_degree"], campos=d["campos"], prefiltered=False, debug=False,
+                          return_accumulation=True)
+        leaves = {k: d[k].requires_grad_(True) for k in leaves_k}
+        means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
+        rast = mod_api(st) if sharded is None else sharded(st)
+        img, radii, acc = rast(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+                               shs=leaves.get("shs"), colors_precomp=leaves.get("colors_precomp"),
+                               scales=leaves.get("scales"), rotations=leaves.get("rotations"))
+        (img * d["dL_dpix"]).sum().backward()
+        out_host["image"].copy_(img.detach(), non_blocking=True)
+        out_host["means2D"].copy_(means2D.grad, non_blocking=True)
+        for k in leaves_k:
+            out_host[k].copy_(leaves[k].grad, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()     # the step's result is on the host
+    return step, h2d, d2h
+
+
+def cpu_baseline(cfg_name, kw, threads=None, frac=None):
+    """The CPU oracle on a bounded sample of the workload: same camera / image, a seeded subsample of the cloud."""
+    from oracle import cpu_oracle
+    P_full = kw["P"]
+    frac = frac or min(1.0, 300_000 / P_full)
+    kw2 = dict(kw); kw2["P"] = max(1000, int(P_full * frac))
+    scene = synthetic.make_scene(**kw2)
+    if threads:
+        cpu_oracle.set_num_threads(threads)
+    nthreads = cpu_oracle.num_threads()
+    cpu_oracle.forward(synthetic.make_scene(P=2000, W=64, H=64, sh_degree=None, seed=0))   # load + warm
+    t0 = time.perf_counter(); st = cpu_oracle.forward(scene); t1 = time.perf_counter()
+    cpu_oracle.backward(st, scene["dL_dpix"]); t2 = time.perf_counter()
+    N = scene["image_width"] * scene["image_height"]
+    return {"value": kw2["P"] * N / (t2 - t0), "unit": "gaussians*pixels/s", "cores": nthreads, "kind": "port",
+            "sample": f"{cfg_name} camera/image, seeded cloud of P={kw2['P']} ({frac:.3f} of the workload), "
+                      f"1 fwd+bwd: fwd {1e3 * (t1 - t0):.0f} ms, bwd {1e3 * (t2 - t1):.0f} ms, R={st['num_rendered']}",
+            "host_cores": os.cpu_count()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=list(synthetic.CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference" and rank != 0:
+        return 0                                    # the reference has no multi-GPU path: rank 0 alone runs it
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+    if world > 1 and a.impl == "ours":
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    kw = dict(synthetic.CONFIGS[a.config]); kw["seed"] = 0
+    scene = synthetic.make_scene(**kw)
+    d = synthetic.to_device(scene, dev)
+    P, W, H = kw["P"], kw["W"], kw["H"]
+    N = W * H
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    sh_M = scene["shs"].shape[1] if "shs" in scene else 0
+    peak, peak_src = peaks()
+    workload = f"{a.config}: {P} Gaussians, {W}x{H}, " + ("colors_precomp" if sh_M == 0 else f"SH deg {scene['sh_degree']} in-kernel")
+
+    line = {"metric": "gaussians_pixels_per_s (forward+backward rasterize)", "unit": "gaussians*pixels/s",
+            "n_gpus": world if a.impl == "ours" else 1, "steps": a.steps, "warmup": a.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded, SURVEY.md 8d generator)",
+            "config": {"workload": workload, "P": P, "W": W, "H": H, "tiles": T,
+                       "l2": "inputs_larger_than_l2 (per-step working set >= 0.5 GB vs 126 MB L2)",
+                       "parallelism": "single GPU" if world == 1 else f"tile-row bands x{world}, NCCL all-gather (image) + all-reduce (partials)"}}
+
+    sampler = ClockSampler(local_rank)
+
+    # ------------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        from oracle import ref_cuda
+        line["impl"] = "reference"
+        if ref_cuda.available():
+            mod = ref_cuda
+            def step():
+                R, color, radii, geom, binning, img = mod.rasterize_gaussians(*call_args(d))
+                mod.rasterize_gaussians_backward(*backward_args(d, radii, geom, R, binning, img))
+            sampler.start()
+            ms = time_steps(step, a.steps, a.warmup, dev, 1)
+            line.update(value=P * N / (ms * 1e-3), ms_per_step=ms,
+                        reference_kind="unmodified reference CUDA rasterizer compiled for sm_100a (oracle/_ref/libdgr_ref.so), "
+                                       "legacy default stream, run on the GPU: the reference has no CPU implementation of this path")
+            # e2e with the same host-buffer harness, through the reference's own Python surface re-created around its _C
+            if not a.no_e2e:
+                api = make_reference_api(mod)
+                e_step, h2d, d2h = make_e2e_step(api["GaussianRasterizer"], scene, dev, api["GaussianRasterizationSettings"])
+                e_ms = time_steps(e_step, max(3, a.steps // 2), 3, dev, 1)
+                line["e2e"] = {"value": P * N / (e_ms * 1e-3), "unit": line["unit"], "ms_per_step": e_ms,
+                               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+            line["clocks"] = sampler.stop()
+            line["gpu_launches"] = None
+            line["cpu_baseline"] = {"value": None, "kind": "reference", "cores": 0,
+                                    "sample": "n/a: this arm ran the reference's CUDA implementation on the GPU"}
+        else:
+            cb = cpu_baseline(a.config, kw)
+            line.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
+                        reference_kind="oracle/_ref/libdgr_ref.so not present: CPU oracle port on the host cores",
+                        e2e={"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
+    import parallel
+    line["impl"] = "ours"
+    bands = None
+    if world > 1:
+        rows = (H + 15) // 16
+        bands = parallel.partition_tile_rows(rows, world)
+        band = bands[rank]
+
+    if world == 1:
+        state = {}
+        def step():
+            R, color, radii, geom, binning, img = _C.rasterize_gaussians(*call_args(d))
+            grads = _C.rasterize_gaussians_backward(*backward_args(d, radii, geom, R, binning, img))
+            state.update(R=R, radii=radii, geom=geom, binning=binning, img=img)
+    else:
+        state = {}
+        def step():
+            _C.set_tile_row_shard(*band)
+            R, color, radii, geom, binning, img = _C.rasterize_gaussians(*call_args(d))
+            off = (128 - img.data_ptr()) % 128
+            fT = img[off:off + 4 * N].view(torch.float32).view(1, H, W)
+            full = parallel.gather_image_bands(torch.cat([color, fT], 0), bands)
+            bargs = backward_args(d, radii, geom, R, binning, img)
+            accum = _C.rasterize_gaussians_backward_partials(*bargs)
+            parallel.reduce_partials(accum[: P * 12])
+            grads = _C.rasterize_gaussians_backward_finalize(accum, *bargs)
+            _C.set_tile_row_shard(0, 0)
+            state.update(R=R, radii=radii, geom=geom, binning=binning, img=img)
+
+    launches0 = _C.launch_count()
+    sampler.start()
+    ms = time_steps(step, a.steps, a.warmup, dev, world)
+    launches = (_C.launch_count() - launches0) // (a.steps + a.warmup) * a.steps
+    clocks = sampler.stop()
+
+    # separate fwd / bwd times and per-stage times: K profiled steps right after the timed region
+    R = state["R"]
+    V = int((state["radii"] > 0).sum())
+    if world == 1:
+        views = _C.debug_views(state["geom"], state["binning"], state["img"], P, sh_M, W, H, R)
+        ncontrib = views["n_contrib"].view(-1)
+        # instances each tile's composite walks = max n_contrib over the tile's pixels
+        nc = views["n_contrib"].float()
+        pad_h, pad_w = (16 - H % 16) % 16, (16 - W % 16) % 16
+        ncp = torch.nn.functional.pad(nc, (0, pad_w, 0, pad_h))
+        tile_max = ncp.view((H + pad_h) // 16, 16, (W + pad_w) // 16, 16).amax(dim=(1, 3))
+        visited = int(tile_max.sum())
+        blended_sum = int(ncontrib.long().sum())
+    else:
+        visited, blended_sum = 0, 0
+    _C.profile_enable(True)
+    acc, tf, tb = {}, [], []
+    for _ in range(a.steps):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        if world == 1:
+            e0.record()
+            Rr, color, radii, geom, binning, img = _C.rasterize_gaussians(*call_args(d))
+            e1.record()
+            _C.rasterize_gaussians_backward(*backward_args(d, radii, geom, Rr, binning, img))
+            e2.record()
+        else:
+            e0.record(); step(); e1.record(); e2.record()
+        torch.cuda.synchronize(dev)
+        tf.append(e0.elapsed_time(e1)); tb.append(e1.elapsed_time(e2))
+        for k, v in _C.profile_read().items():
+            acc.setdefault(k, []).append(v)
+    _C.profile_enable(False)
+    stage_ms = {k: float(np.mean(v)) for k, v in acc.items()}
+
+    value = P * N / (ms * 1e-3)
+    line.update(value=value, ms_per_step=ms, gpu_launches=int(launches), clocks=clocks,
+                fwd_ms=float(np.median(tf)), bwd_ms=float(np.median(tb)) if world == 1 else None,
+                counts={"P": P, "V": V, "R": int(R), "N": N, "tiles": T, "visited_instances": visited,
+                        "sum_n_contrib": blended_sum})
+    if world == 1:
+        sb = stage_bytes(P, V, R, N, T, sh_M, visited)
+        stages = {k: {"ms": stage_ms[k], "alg_bytes": int(sb[k]), "gbs": sb[k] / (stage_ms[k] * 1e-3) / 1e9,
+                      "frac_of_hbm_peak": sb[k] / (stage_ms[k] * 1e-3) / 1e9 / peak} for k in stage_ms if k in sb}
+        dom = max(stages, key=lambda k: stages[k]["ms"])
+        line["stages"] = stages
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                            "frac": stages[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                            "alg_bytes_per_launch": stages[dom]["alg_bytes"], "launch_ms": stages[dom]["ms"]}
+        Bf, Bb = path_bytes(P, V, R, N, sh_M)
+        line["roofline_path"] = {"bound": "hbm", "B_fwd": int(Bf), "B_bwd": int(Bb), "achieved": (Bf + Bb) / (ms * 1e-3) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": (Bf + Bb) / (ms * 1e-3) / 1e9 / peak,
+                                 "formula": "SURVEY.md 8(d)"}
+    else:
+        line["stages"] = {k: {"ms": v} for k, v in stage_ms.items()}
+        line["bands"] = bands
+
+    # e2e through the public API with host buffers
+    if not a.no_e2e:
+        sharded = None
+        if world > 1:
+            sharded = lambda st: parallel.ShardedGaussianRasterizer(st, bands=bands)
+        e_step, h2d, d2h = make_e2e_step(GaussianRasterizer, scene, dev, GaussianRasterizationSettings, sharded)
+        e_ms = time_steps(e_step, max(3, a.steps // 2), 3, dev, world)
+        line["e2e"] = {"value": P * N / (e_ms * 1e-3), "unit": line["unit"], "ms_per_step": e_ms,
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a.config, kw)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    return 0
+
+
+def make_reference_api(_C):
+    """The reference's Python surface (autograd.Function + nn.Module, __init__.py:46-241) re-created around a
+    `_C`-like module, so that the reference arm's e2e goes through the same kind of public call as ours."""
+    from typing import NamedTuple
+
+    class Settings(NamedTuple):
+        image_height: int; image_width: int; tanfovx: float; tanfovy: float; kernel_size: float
+        subpixel_offset: torch.Tensor; bg: torch.Tensor; scale_modifier: float; viewmatrix: torch.Tensor
+        projmatrix: torch.Tensor; sh_degree: int; campos: torch.Tensor; prefiltered: bool; debug: bool
+        return_accumulation: bool
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, means3D, means2D, sh, colors, opac, scales, rots, cov, s):
+            R, color, radii, geom, binning, img = _C.rasterize_gaussians(
+                s.bg, means3D, colors, opac, scales, rots, s.scale_modifier, cov, s.viewmatrix, s.projmatrix,
+                s.tanfovx, s.tanfovy, s.kernel_size, s.subpixel_offset, s.image_height, s.image_width, sh,
+                s.sh_degree, s.campos, s.prefiltered, s.debug)
+            ctx.s, ctx.R = s, R
+            ctx.save_for_backward(colors, means3D, scales, rots, cov, radii, sh, geom, binning, img)
+            off = (128 - img.data_ptr()) % 128
+            n = 4 * s.image_height * s.image_width
+            acc = img[off:off + n].view(torch.float32).clone().mul_(-1).add_(1).view(s.image_height, s.image_width)
+            return color, radii, acc
+
+        @staticmethod
+        def backward(ctx, g, _1, _2):
+            s = ctx.s
+            colors, means3D, scales, rots, cov, radii, sh, geom, binning, img = ctx.saved_tensors
+            gm2, gc, go, gm3, gcov, gsh, gs, gr = _C.rasterize_gaussians_backward(
+                s.bg, means3D, radii, colors, scales, rots, s.scale_modifier, cov, s.viewmatrix, s.projmatrix,
+                s.tanfovx, s.tanfovy, s.kernel_size, s.subpixel_offset, g, sh, s.sh_degree, s.campos, geom, ctx.R,
+                binning, img, s.debug)
+            return gm3, gm2, gsh, gc, go, gs, gr, gcov, None
+
+    class Rasterizer(torch.nn.Module):
+        def __init__(self, raster_settings):
+            super().__init__()
+            self.raster_settings = raster_settings
+
+        def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                    cov3D_precomp=None):
+            e = torch.Tensor([])
+            return Fn.apply(means3D, means2D, e if shs is None else shs, e if colors_precomp is None else colors_precomp,
+                            opacities, e if scales is None else scales, e if rotations is None else rotations,
+                            e if cov3D_precomp is None else cov3D_precomp, self.raster_settings)
+
+    return {"GaussianRasterizationSettings": Settings, "GaussianRasterizer": Rasterizer}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,6 +167,14 @@ int gsr_forward_recolor(const GsrForwardArgs* args, const void* geom_buffer,
 /* -- backward ---------------------------------------------------------------------------- */
 size_t gsr_backward_scratch_bytes(int P);
 int    gsr_backward(const GsrBackwardArgs* args, void* stream);
+/* The two halves of gsr_backward(), for the tile-row sharded (multi-GPU) path where the
+ * per-Gaussian partial sums of all shards are added (NCCL all-reduce over accum_scratch, a dense
+ * [P][12] fp32 array starting at the first 256-byte aligned address) between them:
+ *   partials: zero accum_scratch, run the per-tile backward composite of this shard into it
+ *             (needs dL_dpix, img/binning buffers; writes no output tensor)
+ *   finalize: per-Gaussian chain rule from accum_scratch to every output tensor                     */
+int    gsr_backward_partials(const GsrBackwardArgs* args, void* stream);
+int    gsr_backward_finalize(const GsrBackwardArgs* args, void* stream);
 
 /* -- markVisible (rasterizer_impl.cu:54-66,141-153): present[i] = (view*p).z > 0.2 ------- */
 int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix,
@@ -185,6 +193,16 @@ int gsr_binning_views(const void* binning_buffer, int num_rendered, const uint32
 int gsr_geom_views(const void* geom_buffer, int P, int M, const float** depths,
                    const float** records, const uint32_t** tiles_touched, const float** rgb);
 int gsr_get_stats(const void* geom_buffer, int P, int M, void* stream, GsrStats* out);
+
+/* Optional per-stage device timing (cudaEvents on the caller's stream around each stage of the
+ * next forward / backward calls).  The caller synchronises the stream, then reads the stage times of
+ * the most recent calls in milliseconds (-1 for stages that did not run).  Not thread-safe.        */
+void        gsr_profile_enable(int on);
+int         gsr_profile_stage_count(void);
+const char* gsr_profile_stage_name(int i);
+int         gsr_profile_read(float* ms, int n);
+/* number of kernels this library has launched in this process                                     */
+unsigned long long gsr_launch_count(void);
 
 #ifdef __cplusplus
 }

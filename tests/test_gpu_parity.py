@@ -1,0 +1,334 @@
+"""GPU parity tests (run on a B200 with ``-m gpu``): the CUDA path, called through the C ABI
+(``diff_gaussian_rasterization._C`` is a ctypes shim over ``include/gsrast.h``) and through the drop-in Python
+API, against (a) the committed golden vectors of the reference, (b) the compiled reference itself when
+``oracle/_ref/libdgr_ref.so`` travelled with the snapshot, (c) the CPU oracle; plus size-independent
+properties at BASELINE.json's full sizes.
+
+Bars (BASELINE.json north star): tile / sort indices bit-exact; pixels within 1e-4; gradients within 1e-3
+of the largest gradient magnitude (the reference's own float-atomic run-to-run noise is ~1e-6).
+"""
+import numpy as np
+import pytest
+import torch
+
+import synthetic
+from golden_util import GRAD_NAMES, GRAD_TOL, PIX_TOL, bits, load_case, rel_err
+from make_golden import CASES, backward_args, call_args
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    from diff_gaussian_rasterization import _C
+    return _C
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def run_ours(C, d):
+    R, color, radii, geom, binning, img = C.rasterize_gaussians(*call_args(d))
+    P = d["means3D"].shape[0]
+    M = d["shs"].shape[1] if "shs" in d else 0
+    v = C.debug_views(geom, binning, img, P, M, d["image_width"], d["image_height"], R) if P else {}
+    grads = C.rasterize_gaussians_backward(*backward_args(d, radii, geom, R, binning, img))
+    torch.cuda.synchronize()
+    return dict(R=R, color=color, radii=radii, views=v, grads=dict(zip(GRAD_NAMES, grads)), bufs=(geom, binning, img))
+
+
+# ------------------------------------------------------------------------------------------------------
+# (a) golden vectors of the reference
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CASES))
+def test_against_reference_golden(C, dev, name):
+    scene, gold = load_case(name)
+    o = run_ours(C, synthetic.to_device(scene, dev))
+    v = o["views"]
+    vis = gold["radii"] > 0
+    # integer artefacts: bit-exact
+    assert o["R"] == int(gold["num_rendered"])
+    assert np.array_equal(o["radii"].cpu().numpy(), gold["radii"])
+    assert np.array_equal(v["tiles_touched"].cpu().numpy()[vis], gold["tiles_touched"][vis])
+    assert np.array_equal(v["point_list"].cpu().numpy(), gold["point_list"]), "sorted instance list differs"
+    assert np.array_equal(v["ranges"].cpu().numpy(), gold["ranges"])
+    assert np.array_equal(v["n_contrib"].cpu().numpy(), gold["n_contrib"])
+    # projected state: same bits (numerics notes N1/N2)
+    rec = v["records"].cpu().numpy()
+    assert np.array_equal(bits(v["depths"].cpu().numpy()[vis]), bits(gold["depths"][vis]))
+    assert np.array_equal(bits(np.ascontiguousarray(rec[vis][:, 0:2])), bits(gold["means2D"][vis]))
+    assert np.array_equal(bits(np.ascontiguousarray(rec[vis][:, 2:6])), bits(gold["conic_opacity"][vis]))
+    if "shs" in scene:
+        assert np.array_equal(bits(v["rgb"].cpu().numpy()[vis]), bits(gold["rgb"][vis]))
+    # pixels: tolerance 1e-4 (measured: identical bits)
+    assert np.abs(o["color"].cpu().numpy() - gold["out_color"]).max() <= PIX_TOL
+    assert np.abs(v["final_T"].cpu().numpy() - gold["final_T"]).max() <= PIX_TOL
+    # gradients: 1e-3 of the tensor's largest magnitude
+    for n in GRAD_NAMES:
+        if gold[n].size:
+            assert rel_err(o["grads"][n].cpu().numpy().reshape(gold[n].shape), gold[n]) < GRAD_TOL, n
+
+
+# ------------------------------------------------------------------------------------------------------
+# (b) the compiled reference, same process, same tensors
+# ------------------------------------------------------------------------------------------------------
+REF_SCENES = [
+    dict(P=200_000, W=800, H=800, sh_degree=3, seed=21),
+    dict(P=300_000, W=1000, H=700, sh_degree=None, seed=22),
+    dict(P=50_000, W=333, H=211, sh_degree=2, seed=23, subpixel_jitter=0.5, bg=(1.0, 0.5, 0.25)),
+    dict(P=20_000, W=640, H=360, sh_degree=None, seed=24, scale_range=(0.05, 0.5)),       # huge splats
+    dict(P=100_000, W=512, H=512, sh_degree=None, seed=25, normalize_rot=False),
+    dict(P=60_000, W=400, H=300, sh_degree=None, seed=26, cov3D_precomp=True),
+]
+
+
+@pytest.mark.parametrize("kw", REF_SCENES, ids=lambda k: f"P{k['P']}_{k['W']}x{k['H']}_s{k['seed']}")
+def test_against_compiled_reference(C, dev, kw):
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libdgr_ref.so not present")
+    scene = synthetic.make_scene(**kw)
+    d = synthetic.to_device(scene, dev)
+    o = run_ours(C, d)
+    R, color, radii, geom, binning, img = ref_cuda.rasterize_gaussians(*call_args(d))
+    P = d["means3D"].shape[0]
+    rv = ref_cuda.debug_views(geom, binning, img, P, d["image_width"], d["image_height"], R)
+    rg = dict(zip(GRAD_NAMES, ref_cuda.rasterize_gaussians_backward(*backward_args(d, radii, geom, R, binning, img))))
+    rg2 = dict(zip(GRAD_NAMES, ref_cuda.rasterize_gaussians_backward(*backward_args(d, radii, geom, R, binning, img))))
+    torch.cuda.synchronize()
+    v = o["views"]
+    assert o["R"] == R
+    assert torch.equal(o["radii"], radii)
+    assert torch.equal(v["point_list"], rv["point_list"])
+    assert torch.equal(v["ranges"], rv["ranges"])
+    assert torch.equal(v["n_contrib"], rv["n_contrib"])
+    vis = radii > 0
+    assert torch.equal(v["depths"][vis].view(torch.int32), rv["depths"][vis].view(torch.int32))
+    assert torch.equal(v["records"][vis][:, 0:2].contiguous().view(torch.int32), rv["means2D"][vis].view(torch.int32))
+    assert torch.equal(v["records"][vis][:, 2:6].contiguous().view(torch.int32),
+                       rv["conic_opacity"][vis].view(torch.int32))
+    assert float((o["color"] - color).abs().max()) <= PIX_TOL
+    for n in GRAD_NAMES:
+        if rg[n].numel() == 0:
+            continue
+        scale = float(rg[n].abs().max()) + 1e-30
+        ours_err = float((o["grads"][n].view_as(rg[n]) - rg[n]).abs().max()) / scale
+        ref_noise = float((rg2[n] - rg[n]).abs().max()) / scale     # float-atomic order noise of the reference itself
+        assert ours_err < GRAD_TOL, (n, ours_err, ref_noise)
+
+
+# ------------------------------------------------------------------------------------------------------
+# (c) the CPU oracle
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [dict(P=20_000, W=320, H=240, sh_degree=3, seed=31),
+                                dict(P=30_000, W=300, H=200, sh_degree=None, seed=32, subpixel_jitter=0.3)])
+def test_against_cpu_oracle(C, dev, kw):
+    from oracle import cpu_oracle
+    scene = synthetic.make_scene(**kw)
+    o = run_ours(C, synthetic.to_device(scene, dev))
+    st = cpu_oracle.forward(scene)
+    g = cpu_oracle.backward(st, scene["dL_dpix"])
+    assert o["R"] == st["num_rendered"]
+    assert np.array_equal(o["radii"].cpu().numpy(), st["radii"])
+    assert np.array_equal(o["views"]["point_list"].cpu().numpy(), st["point_list"].astype(np.int32))
+    assert np.array_equal(o["views"]["ranges"].cpu().numpy(), st["ranges"].astype(np.int32))
+    assert np.abs(o["color"].cpu().numpy() - st["out_color"]).max() < PIX_TOL
+    ne = (o["views"]["n_contrib"].cpu().numpy() != st["n_contrib"].astype(np.int32)).mean()
+    assert ne <= 1e-4      # CUDA expf vs glibc expf can flip an alpha threshold
+    for n in GRAD_NAMES:
+        ref = g[n]
+        if ref.size:
+            assert rel_err(o["grads"][n].cpu().numpy().reshape(ref.shape), ref) < GRAD_TOL, n
+
+
+# ------------------------------------------------------------------------------------------------------
+# drop-in Python API (what wildgaussians/method.py:1529-1631 does)
+# ------------------------------------------------------------------------------------------------------
+def _settings(d, debug=False):
+    from diff_gaussian_rasterization import GaussianRasterizationSettings
+    return GaussianRasterizationSettings(
+        image_height=d["image_height"], image_width=d["image_width"], tanfovx=d["tanfovx"], tanfovy=d["tanfovy"],
+        kernel_size=d["kernel_size"], subpixel_offset=d["subpixel_offset"], bg=d["bg"], scale_modifier=1.0,
+        viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"], sh_degree=d["sh_degree"], campos=d["campos"],
+        prefiltered=False, debug=debug, return_accumulation=True)
+
+
+def test_autograd_two_passes_like_method_py(C, dev):
+    """Two rasterizer calls on the same geometry (raw + toned colours), one backward: the shared
+    `screenspace_points` gradient accumulates both passes (method.py:1495,1573-1611,1470-1477)."""
+    from diff_gaussian_rasterization import GaussianRasterizer
+    scene = synthetic.make_scene(P=30_000, W=320, H=208, sh_degree=None, seed=41)
+    d = synthetic.to_device(scene, dev)
+    leaves = {k: d[k].clone().requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations")}
+    col_a = d["colors_precomp"].clone().requires_grad_(True)
+    col_b = (1.0 - d["colors_precomp"]).clone().requires_grad_(True)
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True) + 0
+    means2D.retain_grad()
+    rast = GaussianRasterizer(_settings(d))
+    kw = dict(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], scales=leaves["scales"],
+              rotations=leaves["rotations"], shs=None, cov3D_precomp=None)
+    img_a, radii, acc = rast(colors_precomp=col_a, **kw)
+    img_b, radii_b, acc_b = rast(colors_precomp=col_b, **kw)
+    assert img_a.shape == (3, 208, 320) and radii.dtype == torch.int32 and acc.shape == (208, 320)
+    assert torch.equal(radii, radii_b) and torch.equal(acc, acc_b)
+    (img_a * d["dL_dpix"]).sum().backward(retain_graph=True)
+    g_a = {k: v.grad.clone() for k, v in leaves.items()}
+    m2d_a = means2D.grad.clone()
+    (img_b * d["dL_dpix"]).sum().backward()
+    torch.cuda.synchronize()
+    # reference values from the raw C-level call
+    o_a = run_ours(C, d)
+    d_b = dict(d); d_b["colors_precomp"] = (1.0 - d["colors_precomp"]).contiguous()
+    o_b = run_ours(C, d_b)
+    assert torch.equal(img_a.detach(), o_a["color"]) and torch.equal(img_b.detach(), o_b["color"])
+    fT = o_a["views"]["final_T"]
+    assert torch.allclose(acc, 1.0 - fT)
+    for k, n in (("means3D", "dL_dmeans3D"), ("scales", "dL_dscales"), ("rotations", "dL_drotations"),
+                 ("opacities", "dL_dopacity")):
+        ref_a = o_a["grads"][n].view_as(g_a[k])
+        assert rel_err(g_a[k].cpu().numpy(), ref_a.cpu().numpy()) < GRAD_TOL
+        both = ref_a + o_b["grads"][n].view_as(ref_a)
+        assert rel_err(leaves[k].grad.cpu().numpy(), both.cpu().numpy()) < GRAD_TOL
+    assert rel_err(m2d_a.cpu().numpy(), o_a["grads"]["dL_dmeans2D"].cpu().numpy()) < GRAD_TOL
+    assert rel_err(col_a.grad.cpu().numpy(), o_a["grads"]["dL_dcolors"].cpu().numpy()) < GRAD_TOL
+    assert (means2D.grad[:, 2] >= 0).all()          # abs-gradient channel
+
+
+def test_sh_path_and_debug_flag(C, dev):
+    from diff_gaussian_rasterization import GaussianRasterizer
+    scene = synthetic.make_scene(P=5_000, W=160, H=96, sh_degree=2, seed=42)
+    d = synthetic.to_device(scene, dev)
+    shs = d["shs"].clone().requires_grad_(True)
+    means2D = torch.zeros_like(d["means3D"], requires_grad=True)
+    img, radii, acc = GaussianRasterizer(_settings(d, debug=True))(
+        means3D=d["means3D"], means2D=means2D, opacities=d["opacities"], shs=shs, scales=d["scales"],
+        rotations=d["rotations"])
+    (img * d["dL_dpix"]).sum().backward()
+    o = run_ours(C, d)
+    assert torch.equal(img.detach(), o["color"])
+    assert rel_err(shs.grad.cpu().numpy(), o["grads"]["dL_dsh"].cpu().numpy()) < GRAD_TOL
+    # coefficients above the active degree (2) get no gradient
+    assert float(shs.grad[:, 9:].abs().max()) == 0.0
+
+
+def test_mark_visible(C, dev):
+    from diff_gaussian_rasterization import GaussianRasterizer
+    scene = synthetic.make_scene(P=10_000, W=64, H=64, sh_degree=None, seed=43)
+    d = synthetic.to_device(scene, dev)
+    vis = GaussianRasterizer(_settings(d)).markVisible(d["means3D"])
+    assert vis.dtype == torch.bool
+    assert torch.equal(vis.cpu(), scene["means3D"][:, 2] > 0.2)
+
+
+# ------------------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------------------
+def test_empty_cloud(C, dev):
+    scene = synthetic.make_scene(P=10, W=70, H=50, sh_degree=None, seed=44, bg=(0.1, 0.2, 0.3))
+    for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp"):
+        scene[k] = scene[k][:0]
+    d = synthetic.to_device(scene, dev)
+    R, color, radii, geom, binning, img = C.rasterize_gaussians(*call_args(d))
+    assert R == 0 and radii.numel() == 0 and color.shape == (3, 50, 70)
+    assert float(color.abs().max()) == 0.0       # the reference skips everything for P == 0 (rasterize_points.cu:83)
+    grads = C.rasterize_gaussians_backward(*backward_args(d, radii, geom, R, binning, img))
+    assert all(g.shape[0] == 0 for g in grads)
+
+
+def test_everything_culled_renders_background(C, dev):
+    scene = synthetic.make_scene(P=1000, W=70, H=50, sh_degree=None, seed=45, bg=(0.1, 0.2, 0.3))
+    scene["means3D"][:, 2] = -scene["means3D"][:, 2].abs() - 1
+    d = synthetic.to_device(scene, dev)
+    o = run_ours(C, d)
+    assert o["R"] == 0 and int(o["radii"].abs().max()) == 0
+    assert torch.allclose(o["color"], d["bg"][:, None, None].expand(3, 50, 70))
+    assert all(float(g.abs().max()) == 0 for g in o["grads"].values() if g.numel())
+
+
+def test_tile_row_shards_compose(C, dev):
+    """The multi-GPU partition: bands rendered separately reproduce the full image bit for bit and their
+    per-Gaussian gradients sum to the full gradients."""
+    scene = synthetic.make_scene(P=40_000, W=300, H=212, sh_degree=None, seed=46)
+    d = synthetic.to_device(scene, dev)
+    full = run_ours(C, d)
+    rows = (212 + 15) // 16
+    parts = []
+    try:
+        for y0, y1 in ((0, 5), (5, 9), (9, rows)):
+            C.set_tile_row_shard(y0, y1)
+            parts.append(((y0, y1), run_ours(C, d)))
+    finally:
+        C.set_tile_row_shard(0, 0)
+    assert sum(p["R"] for _, p in parts) == full["R"]
+    img = torch.zeros_like(full["color"])
+    for (y0, y1), p in parts:
+        assert torch.equal(p["radii"], full["radii"])
+        img[:, 16 * y0:16 * y1] = p["color"][:, 16 * y0:16 * y1]
+    assert torch.equal(img, full["color"])
+    for n in GRAD_NAMES:
+        tot = sum(p["grads"][n] for _, p in parts)
+        if tot.numel():
+            assert rel_err(tot.cpu().numpy(), full["grads"][n].cpu().numpy()) < GRAD_TOL, n
+
+
+def test_prefiltered_violation_raises(C, dev):
+    scene = synthetic.make_scene(P=2000, W=64, H=64, sh_degree=None, seed=47)
+    d = synthetic.to_device(scene, dev)
+    args = list(call_args(d)); args[19] = True
+    with pytest.raises(RuntimeError, match="filtered although prefiltered"):
+        C.rasterize_gaussians(*args)
+
+
+# ------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", ["C2", "C3"])
+def test_full_size_properties(C, dev, cfg):
+    kw = dict(synthetic.CONFIGS[cfg]); kw["seed"] = 0
+    scene = synthetic.make_scene(**kw)
+    d = synthetic.to_device(scene, dev)
+    o = run_ours(C, d)
+    v, R = o["views"], o["R"]
+    W, H = d["image_width"], d["image_height"]
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    tiles = v["tiles_touched"].long()
+    vis = o["radii"] > 0
+    # R is the sum of the tile counts of the rendered Gaussians
+    assert int(tiles[vis].sum()) == R
+    # the tile ranges partition [0, R) in tile order
+    rg = v["ranges"].long()
+    ne = rg[:, 1] > rg[:, 0]
+    assert int((rg[ne, 1] - rg[ne, 0]).sum()) == R
+    starts, ends = rg[ne, 0], rg[ne, 1]
+    assert int(starts[0]) == 0 and int(ends[-1]) == R and torch.equal(starts[1:], ends[:-1])
+    # inside every tile the list is ordered by depth, ties by Gaussian index (stable sort, note N4)
+    pl = v["point_list"].long()
+    depth_bits = v["depths"].view(torch.int32).long()[pl]
+    tile_of = torch.repeat_interleave(torch.arange(T, device=dev)[ne], (ends - starts))
+    key = (tile_of << 32) | depth_bits
+    assert bool((key[1:] >= key[:-1]).all()), "instance list is not (tile, depth) sorted"
+    same = key[1:] == key[:-1]
+    assert bool((pl[1:][same] > pl[:-1][same]).all()), "depth ties are not in Gaussian-index order"
+    # histogram of Gaussian ids in the list == tiles_touched
+    assert torch.equal(torch.bincount(pl, minlength=tiles.numel()), tiles * vis)
+    # n_contrib never exceeds the tile's list length; transmittance in [0, 1]
+    lens = (rg[:, 1] - rg[:, 0]).view((H + 15) // 16, (W + 15) // 16)
+    per_pix = lens.repeat_interleave(16, 0).repeat_interleave(16, 1)[:H, :W]
+    assert bool((v["n_contrib"].long() <= per_pix).all())
+    assert float(v["final_T"].min()) >= 0.0 and float(v["final_T"].max()) <= 1.0
+    # the forward is deterministic: a second run gives the same bits
+    o2 = run_ours(C, d)
+    assert torch.equal(o2["color"], o["color"]) and torch.equal(o2["views"]["point_list"], v["point_list"])
+    # the backward is linear in the upstream gradient
+    d2 = dict(d); d2["dL_dpix"] = 2.0 * d["dL_dpix"]
+    R2, color2, radii2, geom, binning, img = C.rasterize_gaussians(*call_args(d2))
+    g2 = dict(zip(GRAD_NAMES, C.rasterize_gaussians_backward(*backward_args(d2, radii2, geom, R2, binning, img))))
+    for n in ("dL_dmeans3D", "dL_dopacity", "dL_dscales", "dL_dcolors"):
+        if g2[n].numel():
+            assert rel_err(g2[n].cpu().numpy(), 2.0 * o["grads"][n].cpu().numpy()) < GRAD_TOL, n
+    # invisible Gaussians get exactly zero gradient
+    for n in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity"):
+        if o["grads"][n].numel():
+            assert float(o["grads"][n][~vis].abs().max()) == 0.0

@@ -26,6 +26,37 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return (int)e;
 }
 
+
+// ---- optional per-stage device timing (bench.py's roofline numbers come from here) -------------
+// Off by default.  When on, every stage is bracketed by two events on the caller's stream;
+// gsr_profile_read() synchronises nothing itself: the caller synchronises the stream first.
+enum Stage { ST_PREPROCESS_FWD = 0, ST_DEPTH_SORT, ST_OFFSET_SCAN, ST_EMIT, ST_TILE_SORT, ST_TILE_RANGES,
+             ST_RENDER_FWD, ST_RENDER_BWD, ST_PREPROCESS_BWD, ST_COUNT };
+static const char* const k_stage_names[ST_COUNT] = {"preprocess_fwd", "depth_sort", "offset_scan", "emit_instances",
+                                                    "tile_sort", "tile_ranges", "render_fwd", "render_bwd",
+                                                    "preprocess_bwd"};
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[ST_COUNT][2];
+static bool g_prof_ev_ok = false;
+static bool g_prof_used[ST_COUNT];
+static unsigned long long g_launches = 0;
+
+void count_launches(int n) { g_launches += (unsigned long long)n; }
+
+static void prof_begin(int st, cudaStream_t s) {
+    if (!g_prof_on) return;
+    if (!g_prof_ev_ok) {
+        for (int i = 0; i < ST_COUNT; ++i) { cudaEventCreate(&g_prof_ev[i][0]); cudaEventCreate(&g_prof_ev[i][1]); }
+        g_prof_ev_ok = true;
+    }
+    cudaEventRecord(g_prof_ev[st][0], s);
+}
+static void prof_end(int st, cudaStream_t s) {
+    if (!g_prof_on) return;
+    cudaEventRecord(g_prof_ev[st][1], s);
+    g_prof_used[st] = true;
+}
+
 // ---- carving -------------------------------------------------------------------------------
 template <typename T>
 static void take(char*& cur, T*& ptr, size_t count, size_t align = 256) {
@@ -128,6 +159,26 @@ using namespace gsr;
 extern "C" {
 
 int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+
+void gsr_profile_enable(int on) {
+    g_prof_on = on != 0;
+    for (int i = 0; i < ST_COUNT; ++i) g_prof_used[i] = false;
+}
+int gsr_profile_stage_count(void) { return ST_COUNT; }
+const char* gsr_profile_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? k_stage_names[i] : ""; }
+int gsr_profile_read(float* ms, int n) {
+    // elapsed device time of each stage of the most recent forward/backward; -1 for stages not run.
+    // The caller must have synchronised the stream.
+    for (int i = 0; i < n && i < ST_COUNT; ++i) {
+        ms[i] = -1.f;
+        if (g_prof_on && g_prof_ev_ok && g_prof_used[i]) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, g_prof_ev[i][0], g_prof_ev[i][1]) == cudaSuccess) ms[i] = t;
+        }
+    }
+    return 0;
+}
+unsigned long long gsr_launch_count(void) { return g_launches; }
 const char* gsr_last_error(void) { return g_err; }
 
 int gsr_forward_sizes(int P, int M, int W, int H, size_t* geom_bytes, size_t* img_bytes) {
@@ -161,19 +212,25 @@ int gsr_forward_geometry(const GsrForwardArgs* a, void* geom_buffer, void* img_b
     shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
 
     GSR_CUDA(cudaMemsetAsync(g.counters, 0, 8 * sizeof(int32_t), s));
+    prof_begin(ST_PREPROCESS_FWD, s);
     rc = launch_preprocess_fwd(*a, g, ty0, ty1, s);
     if (rc) return rc;
     GSR_STAGE(s, dbg, "preprocess_fwd_kernel");
+    prof_end(ST_PREPROCESS_FWD, s);
 
     // front-to-back order of the Gaussians: stable sort on the depth bits (all 32, u32 compare
     // like the reference's key, rasterizer_impl.cu:104); culled ones carry 0xFFFFFFFF.
+    prof_begin(ST_DEPTH_SORT, s);
     rc = radix_sort_pairs(g.key_a, g.val_a, g.key_b, g.val_b, (size_t)a->P, 0, 32, g.radix_tmp, s, dbg);
     if (rc) return rc;
+    prof_end(ST_DEPTH_SORT, s);
 
     // instance offsets in depth order; offsets[P] = R
+    prof_begin(ST_OFFSET_SCAN, s);
     rc = scan_gathered(g.tiles_touched, g.order, g.offsets, (size_t)a->P, g.radix_tmp + radix_tmp_elems((size_t)a->P), s);
     if (rc) return rc;
     GSR_STAGE(s, dbg, "scan_gathered");
+    prof_end(ST_OFFSET_SCAN, s);
 
     uint32_t R = 0;
     int32_t counters[8];
@@ -224,21 +281,29 @@ int gsr_forward_render(const GsrForwardArgs* a, void* geom_buffer, void* img_buf
         uint32_t* va = even ? b.point_list : bs.val;
         uint32_t* kb = even ? bs.key : b.tile_keys;
         uint32_t* vb = even ? bs.val : b.point_list;
+        prof_begin(ST_EMIT, s);
         rc = launch_emit_instances(g, a->P, gx, ka, va, s);
         if (rc) return rc;
         GSR_STAGE(s, dbg, "emit_instances_kernel");
+        prof_end(ST_EMIT, s);
         // stable partition by tile id: the depth order inside each tile is preserved
+        prof_begin(ST_TILE_SORT, s);
         rc = radix_sort_pairs(ka, va, kb, vb, R, 0, tile_bits, bs.radix_tmp, s, dbg);
         if (rc) return rc;
+        prof_end(ST_TILE_SORT, s);
     }
+    prof_begin(ST_TILE_RANGES, s);
     rc = launch_tile_ranges(b.tile_keys, R, im.ranges, num_tiles, s);
     if (rc) return rc;
     GSR_STAGE(s, dbg, "tile_ranges_kernel");
+    prof_end(ST_TILE_RANGES, s);
 
     const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
+    prof_begin(ST_RENDER_FWD, s);
     rc = launch_render_fwd(*a, g, b, im, colors, ty0, ty1, s);
     if (rc) return rc;
     GSR_STAGE(s, dbg, "render_fwd_kernel");
+    prof_end(ST_RENDER_FWD, s);
     return 0;
 }
 
@@ -291,17 +356,37 @@ int gsr_forward_recolor(const GsrForwardArgs* a, const void* geom_buffer, const 
 
 size_t gsr_backward_scratch_bytes(int P) { return (size_t)(P > 0 ? P : 0) * sizeof(BwdAccum) + 256; }
 
-int gsr_backward(const GsrBackwardArgs* a, void* stream) {
+static int check_bwd_args(const GsrBackwardArgs* a, bool need_pix, bool need_outputs) {
     if (!a) { set_error("args is NULL"); return GSR_E_INVALID; }
     if (a->P < 0 || a->W <= 0 || a->H <= 0 || a->R < 0) { set_error("bad sizes"); return GSR_E_INVALID; }
     if (a->P == 0) return 0;
-    if (!a->means3D || !a->radii || !a->viewmatrix || !a->projmatrix || !a->background || !a->subpixel_offset ||
-        !a->geom_buffer || !a->img_buffer || !a->dL_dpix || !a->accum_scratch || !a->dL_dmean2D || !a->dL_dopacity ||
-        !a->dL_dcolor || !a->dL_dmean3D) { set_error("a required pointer is NULL"); return GSR_E_INVALID; }
-    if (a->R > 0 && !a->binning_buffer) { set_error("binning_buffer is NULL"); return GSR_E_INVALID; }
-    if (a->shs && (!a->dL_dsh || !a->campos || a->M <= 0)) { set_error("shs given but dL_dsh / campos missing"); return GSR_E_INVALID; }
-    if (a->scales && (!a->rotations || !a->dL_dscale || !a->dL_drot)) { set_error("scales given but rotations / dL_dscale / dL_drot missing"); return GSR_E_INVALID; }
-    if (!a->scales && !a->cov3D_precomp) { set_error("neither scales nor cov3D_precomp"); return GSR_E_INVALID; }
+    if (!a->means3D || !a->radii || !a->viewmatrix || !a->projmatrix || !a->geom_buffer || !a->accum_scratch) {
+        set_error("a required pointer is NULL");
+        return GSR_E_INVALID;
+    }
+    if (need_pix) {
+        if (!a->background || !a->subpixel_offset || !a->img_buffer || !a->dL_dpix) { set_error("a required pointer is NULL"); return GSR_E_INVALID; }
+        if (a->R > 0 && !a->binning_buffer) { set_error("binning_buffer is NULL"); return GSR_E_INVALID; }
+    }
+    if (need_outputs) {
+        if (!a->dL_dmean2D || !a->dL_dopacity || !a->dL_dcolor || !a->dL_dmean3D) { set_error("a required output pointer is NULL"); return GSR_E_INVALID; }
+        if (a->shs && (!a->dL_dsh || !a->campos || a->M <= 0)) { set_error("shs given but dL_dsh / campos missing"); return GSR_E_INVALID; }
+        if (a->scales && (!a->rotations || !a->dL_dscale || !a->dL_drot)) { set_error("scales given but rotations / dL_dscale / dL_drot missing"); return GSR_E_INVALID; }
+        if (!a->scales && !a->cov3D_precomp) { set_error("neither scales nor cov3D_precomp"); return GSR_E_INVALID; }
+    }
+    return 0;
+}
+
+static BwdAccum* accum_of(const GsrBackwardArgs* a) {
+    char* cur = (char*)a->accum_scratch;
+    BwdAccum* accum;
+    take(cur, accum, (size_t)a->P);
+    return accum;
+}
+
+int gsr_backward_partials(const GsrBackwardArgs* a, void* stream) {
+    int rc = check_bwd_args(a, true, false);
+    if (rc || a->P == 0) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const bool dbg = a->debug != 0;
     GeomState g;
@@ -312,23 +397,39 @@ int gsr_backward(const GsrBackwardArgs* a, void* stream) {
     carve_bin((char*)a->binning_buffer, (size_t)a->R, &b);
     int ty0, ty1;
     shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
-
-    char* cur = (char*)a->accum_scratch;
-    BwdAccum* accum;
-    take(cur, accum, (size_t)a->P);
+    BwdAccum* accum = accum_of(a);
     GSR_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * sizeof(BwdAccum), s));
-
     const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
-    int rc = 0;
     if (a->R > 0) {
+        prof_begin(ST_RENDER_BWD, s);
         rc = launch_render_bwd(*a, g, b, im, colors, accum, ty0, ty1, s);
         if (rc) return rc;
         GSR_STAGE(s, dbg, "render_bwd_kernel");
+        prof_end(ST_RENDER_BWD, s);
     }
-    rc = launch_preprocess_bwd(*a, g, accum, s);
-    if (rc) return rc;
-    GSR_STAGE(s, dbg, "preprocess_bwd_kernel");
     return 0;
+}
+
+int gsr_backward_finalize(const GsrBackwardArgs* a, void* stream) {
+    int rc = check_bwd_args(a, false, true);
+    if (rc || a->P == 0) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    GeomState g;
+    carve_geom((char*)a->geom_buffer, a->P, a->M, &g);
+    prof_begin(ST_PREPROCESS_BWD, s);
+    rc = launch_preprocess_bwd(*a, g, accum_of(a), s);
+    if (rc) return rc;
+    GSR_STAGE(s, a->debug != 0, "preprocess_bwd_kernel");
+    prof_end(ST_PREPROCESS_BWD, s);
+    return 0;
+}
+
+int gsr_backward(const GsrBackwardArgs* a, void* stream) {
+    int rc = check_bwd_args(a, true, true);
+    if (rc || a->P == 0) return rc;
+    rc = gsr_backward_partials(a, stream);
+    if (rc) return rc;
+    return gsr_backward_finalize(a, stream);
 }
 
 int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
@@ -404,6 +505,7 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s) {
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+    count_launches(1);
     return 0;
 }
 

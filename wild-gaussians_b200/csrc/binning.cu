@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int grid_x, 
 int launch_emit_instances(const GeomState& g, int P, int gx, uint32_t* keys, uint32_t* vals, cudaStream_t s) {
     if (P == 0) return 0;
     emit_instances_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, gx, g.order, g.offsets, g.rect, keys, vals);
+    count_launches(1);
     return 0;
 }
 
@@ -81,6 +82,7 @@ int launch_tile_ranges(const uint32_t* sorted_tile_keys, size_t R, uint2* ranges
     GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
     if (R == 0) return 0;
     tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(sorted_tile_keys, R, ranges);
+    count_launches(1);
     return 0;
 }
 

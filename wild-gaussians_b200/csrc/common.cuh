@@ -16,6 +16,7 @@ constexpr float NEAR_Z = 0.2f;        // near cull (reference auxiliary.h:154)
 // error plumbing
 // ----------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // kernels launched by this library (bench.py's gpu_launches)
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define GSR_CUDA(expr)                                                        \

@@ -397,6 +397,7 @@ int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, const Bw
     p.dL_dcolor = a.dL_dcolor; p.dL_dmean3D = a.dL_dmean3D; p.dL_dcov3D = a.dL_dcov3D;
     p.dL_dsh = a.dL_dsh; p.dL_dscale = a.dL_dscale; p.dL_drot = a.dL_drot;
     preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(p);
+    count_launches(1);
     return 0;
 }
 

@@ -226,6 +226,7 @@ int launch_preprocess_fwd(const GsrForwardArgs& a, const GeomState& g, int ty0, 
     p.sort_key = g.key_a; p.sort_val = g.val_a; p.counters = g.counters;
     const int blocks = (a.P + 255) / 256;
     preprocess_fwd_kernel<<<blocks, 256, 0, s>>>(p);
+    count_launches(1);
     return 0;
 }
 

@@ -200,10 +200,13 @@ int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t
         uint32_t* kout = a_to_b ? key_b : key_a;
         uint32_t* vout = a_to_b ? val_b : val_a;
         radix_hist_kernel<<<ctas, RS_THREADS, 0, s>>>(kin, n, shift, mask, hist, ctas);
+        count_launches(1);
         GSR_STAGE(s, debug, "radix_hist_kernel");
         radix_rowscan_kernel<<<RADIX, 1024, 0, s>>>(hist, ctas, total);
+        count_launches(1);
         GSR_STAGE(s, debug, "radix_rowscan_kernel");
         radix_scatter_kernel<true><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, total, ctas);
+        count_launches(1);
         GSR_STAGE(s, debug, "radix_scatter_kernel");
     }
     return 0;
@@ -327,8 +330,11 @@ int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, s
     }
     const uint32_t m = (uint32_t)((n + SC_CHUNK - 1) / SC_CHUNK);
     scan_reduce_kernel<<<m, SC_THREADS, 0, s>>>(counts, perm, n, tmp);
+    count_launches(1);
     scan_partials_kernel<<<1, 1024, 0, s>>>(tmp, m);
+    count_launches(1);
     scan_apply_kernel<<<m, SC_THREADS, 0, s>>>(counts, perm, n, tmp, m, out);
+    count_launches(1);
     GSR_CUDA(cudaGetLastError());
     return 0;
 }

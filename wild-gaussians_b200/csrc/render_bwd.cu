@@ -248,6 +248,7 @@ int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinSta
     if (ty1 <= ty0) return 0;
     dim3 grid(p.grid_x, ty1 - ty0, 1);
     render_bwd_kernel<<<grid, RB_THREADS, 0, s>>>(p);
+    count_launches(1);
     return 0;
 }
 

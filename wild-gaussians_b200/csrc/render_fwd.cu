@@ -162,6 +162,7 @@ int launch_render_fwd(const GsrForwardArgs& a, const GeomState& g, const BinStat
     if (ty1 <= ty0) return 0;
     dim3 grid(p.grid_x, ty1 - ty0, 1);
     render_fwd_kernel<<<grid, RF_THREADS, 0, s>>>(p);
+    count_launches(1);
     return 0;
 }
 

@@ -69,13 +69,23 @@ def _load():
     lib.gsr_backward_scratch_bytes.argtypes = [c_int]
     lib.gsr_backward_scratch_bytes.restype = c_size_t
     lib.gsr_backward.argtypes = [POINTER(GsrBackwardArgs), c_void_p]
+    lib.gsr_backward_partials.argtypes = [POINTER(GsrBackwardArgs), c_void_p]
+    lib.gsr_backward_finalize.argtypes = [POINTER(GsrBackwardArgs), c_void_p]
     lib.gsr_mark_visible.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsr_img_views.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
     lib.gsr_binning_views.argtypes = [c_void_p, c_int, POINTER(c_void_p)]
     lib.gsr_geom_views.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
     lib.gsr_get_stats.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(GsrStats)]
+    lib.gsr_profile_enable.argtypes = [c_int]
+    lib.gsr_profile_enable.restype = None
+    lib.gsr_profile_stage_count.restype = c_int
+    lib.gsr_profile_stage_name.argtypes = [c_int]
+    lib.gsr_profile_stage_name.restype = c_char_p
+    lib.gsr_profile_read.argtypes = [POINTER(c_float), c_int]
+    lib.gsr_launch_count.restype = ctypes.c_ulonglong
     for name in ("gsr_forward_sizes", "gsr_forward_geometry", "gsr_binning_sizes", "gsr_forward_render",
-                 "gsr_forward_recolor", "gsr_backward", "gsr_mark_visible", "gsr_img_views", "gsr_binning_views",
+                 "gsr_forward_recolor", "gsr_backward", "gsr_backward_partials", "gsr_backward_finalize",
+                 "gsr_mark_visible", "gsr_img_views", "gsr_binning_views",
                  "gsr_geom_views", "gsr_get_stats"):
         getattr(lib, name).restype = c_int
     if lib.gsr_abi_version() != 1:
@@ -183,40 +193,42 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     return R.value, out_color, radii, geom, binning, img
 
 
-def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
-                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size,
-                                 subpixel_offset, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                 imageBuffer, debug):
-    """Drop-in for ``RasterizeGaussiansBackwardCUDA`` (rasterize_points.cu:121-204).
-
-    Returns ``(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)``.
-    """
+def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rotations, scale_modifier,
+                   cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
+                   dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug):
+    """mode: "both" (gsr_backward), "partials" (returns the [P,12] accumulator), "finalize" (consumes it)."""
     dev = means3D.device
     P = int(means3D.size(0))
     H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
     M = int(sh.size(1)) if sh.numel() != 0 else 0
     with torch.cuda.device(dev):
         f32 = dict(dtype=torch.float32, device=dev)
-        # every row of every output is written by the kernel: empty, not zeros
-        alloc = torch.empty if P > 0 else torch.zeros
-        dL_dmeans3D = alloc((P, 3), **f32)
-        dL_dmeans2D = alloc((P, 3), **f32)
-        dL_dcolors = alloc((P, NUM_CHANNELS), **f32)
-        dL_dopacity = alloc((P, 1), **f32)
-        dL_dcov3D = alloc((P, 6), **f32)
-        dL_dsh = alloc((P, M, 3), **f32)
         have_scales = scales.numel() != 0
-        dL_dscales = alloc((P, 3), **f32) if have_scales else torch.zeros((P, 3), **f32)
-        dL_drotations = alloc((P, 4), **f32) if have_scales else torch.zeros((P, 4), **f32)
+        outs = None
+        if mode != "partials":
+            # every row of every output is written by the kernel: empty, not zeros
+            alloc = torch.empty if P > 0 else torch.zeros
+            dL_dmeans3D = alloc((P, 3), **f32)
+            dL_dmeans2D = alloc((P, 3), **f32)
+            dL_dcolors = alloc((P, NUM_CHANNELS), **f32)
+            dL_dopacity = alloc((P, 1), **f32)
+            dL_dcov3D = alloc((P, 6), **f32)
+            dL_dsh = alloc((P, M, 3), **f32)
+            dL_dscales = alloc((P, 3), **f32) if have_scales else torch.zeros((P, 3), **f32)
+            dL_drotations = alloc((P, 4), **f32) if have_scales else torch.zeros((P, 4), **f32)
+            outs = (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
         if P == 0:
-            return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+            return outs if mode != "partials" else torch.zeros((0, 12), **f32)
 
         keep = [_f32c(t, dev) for t in (background, means3D, colors, scales, rotations, cov3D_precomp, viewmatrix,
                                         projmatrix, subpixel_offset, dL_dout_color, sh, campos)]
         (background, means3D, colors, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, subpixel_offset,
          dL_dout_color, sh, campos) = keep
         radii = radii.contiguous()
-        scratch = torch.empty((_lib.gsr_backward_scratch_bytes(P),), dtype=torch.uint8, device=dev)
+        if accum is None:
+            # [P,12] fp32 partial sums; +64 floats so a 256-byte aligned view of P rows always fits
+            accum = torch.empty((P * 12 + 64,), **f32)
+        assert accum.data_ptr() % 256 == 0 and accum.numel() >= P * 12
 
         a = GsrBackwardArgs()
         a.P, a.D, a.M, a.R, a.W, a.H = P, int(degree), M, int(R), W, H
@@ -229,16 +241,42 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
         a.geom_buffer = _ptr(geomBuffer); a.binning_buffer = _ptr(binningBuffer); a.img_buffer = _ptr(imageBuffer)
         a.dL_dpix = _ptr(dL_dout_color); a.debug = int(bool(debug))
         a.tile_y0, a.tile_y1 = _shard
-        a.accum_scratch = scratch.data_ptr()
-        a.dL_dmean2D = dL_dmeans2D.data_ptr(); a.dL_dconic = None
-        a.dL_dopacity = dL_dopacity.data_ptr(); a.dL_dcolor = dL_dcolors.data_ptr()
-        a.dL_dmean3D = dL_dmeans3D.data_ptr(); a.dL_dcov3D = dL_dcov3D.data_ptr()
-        a.dL_dsh = _ptr(dL_dsh)
-        a.dL_dscale = dL_dscales.data_ptr() if have_scales else None
-        a.dL_drot = dL_drotations.data_ptr() if have_scales else None
-        _check(_lib.gsr_backward(byref(a), _stream(dev)), "gsr_backward")
-        del scratch
-    return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+        a.accum_scratch = accum.data_ptr()
+        if outs is not None:
+            a.dL_dmean2D = dL_dmeans2D.data_ptr(); a.dL_dconic = None
+            a.dL_dopacity = dL_dopacity.data_ptr(); a.dL_dcolor = dL_dcolors.data_ptr()
+            a.dL_dmean3D = dL_dmeans3D.data_ptr(); a.dL_dcov3D = dL_dcov3D.data_ptr()
+            a.dL_dsh = _ptr(dL_dsh)
+            a.dL_dscale = dL_dscales.data_ptr() if have_scales else None
+            a.dL_drot = dL_drotations.data_ptr() if have_scales else None
+        fn = {"both": _lib.gsr_backward, "partials": _lib.gsr_backward_partials,
+              "finalize": _lib.gsr_backward_finalize}[mode]
+        _check(fn(byref(a), _stream(dev)), "gsr_backward" + ("" if mode == "both" else "_" + mode))
+    return accum if mode == "partials" else outs
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size,
+                                 subpixel_offset, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                 imageBuffer, debug):
+    """Drop-in for ``RasterizeGaussiansBackwardCUDA`` (rasterize_points.cu:121-204).
+
+    Returns ``(dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)``.
+    """
+    return _backward_impl("both", None, background, means3D, radii, colors, scales, rotations, scale_modifier,
+                          cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
+                          dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug)
+
+
+def rasterize_gaussians_backward_partials(*args):
+    """First half of the backward for the tile-row sharded path: this shard's per-Gaussian partial sums as a
+    flat fp32 tensor whose first ``P*12`` entries are the ``[P,12]`` accumulator (same 23 arguments)."""
+    return _backward_impl("partials", None, *args)
+
+
+def rasterize_gaussians_backward_finalize(accum, *args):
+    """Second half: per-Gaussian chain rule from the (all-reduced) accumulator to the 8 gradient tensors."""
+    return _backward_impl("finalize", accum, *args)
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):
@@ -296,3 +334,20 @@ def stats(geomBuffer, P, M):
     s = GsrStats()
     _check(_lib.gsr_get_stats(geomBuffer.data_ptr(), P, M, _stream(geomBuffer.device), byref(s)), "gsr_get_stats")
     return {"num_rendered": s.num_rendered, "num_visible": s.num_visible}
+
+
+def profile_enable(on: bool) -> None:
+    """Per-stage device timing of the following calls (cudaEvents inside the library)."""
+    _lib.gsr_profile_enable(int(bool(on)))
+
+
+def profile_read() -> dict:
+    """Stage name -> milliseconds of the most recent forward/backward (synchronise first)."""
+    n = _lib.gsr_profile_stage_count()
+    buf = (c_float * n)()
+    _lib.gsr_profile_read(buf, n)
+    return {_lib.gsr_profile_stage_name(i).decode(): float(buf[i]) for i in range(n) if buf[i] >= 0}
+
+
+def launch_count() -> int:
+    return int(_lib.gsr_launch_count())

@@ -1,0 +1,158 @@
+"""Screen-space sharding of one rasterization across the GPUs of a box.
+
+The reference is single-GPU (``method.py:113-117``); this is the new multi-GPU path BASELINE.json asks
+for.  One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).  Every rank holds all P
+Gaussians (replicated parameters, as in single-GPU training) and
+
+* forward: projects all Gaussians (cheap, HBM-bound) but bins / sorts / composites only its band of tile
+  rows ``[y0, y1)``; because the sort key's major field is the tile id, a band's instance list is exactly
+  the corresponding slice of the single-GPU list, so its pixels are bit-identical to the single-GPU image.
+  One all-gather of the colour (+ transmittance) bands assembles the full image on every rank.
+* backward: the upstream gradient image is replicated (every rank evaluates the loss on the full image);
+  each rank runs the backward composite on its band into a ``[P,12]`` partial-sum array; one all-reduce (sum)
+  adds the partials of Gaussians that straddle bands -- a plain all-gather would be wrong -- and every rank then runs the
+  per-Gaussian chain rule on the summed partials, yielding the full gradients everywhere.
+
+The collective helpers below are backend-agnostic (tested with gloo on CPU, world_size 2).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+TILE = 16
+
+
+def partition_tile_rows(num_tile_rows: int, world_size: int, weights: Sequence[float] | None = None) -> List[Tuple[int, int]]:
+    """Contiguous bands of tile rows, one per rank.  With ``weights`` (e.g. instances per tile row from the
+    previous iteration) the bands are chosen to equalise the weight; otherwise the row counts."""
+    import bisect
+    n, w = int(num_tile_rows), int(world_size)
+    assert n >= 0 and w >= 1
+    if weights is None or float(sum(weights)) <= 0.0:
+        weights = [1.0] * n
+    assert len(weights) == n
+    cum = [0.0]
+    for x in weights:
+        cum.append(cum[-1] + float(x))
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, w):
+        # first row boundary at which the running weight reaches r/w of the total
+        e = bisect.bisect_left(cum, total * r / w - 1e-9 * max(1.0, total))
+        cuts.append(min(n, max(e, cuts[-1])))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(w)]
+
+
+def band_pixel_rows(band: Tuple[int, int], H: int) -> Tuple[int, int]:
+    return min(H, band[0] * TILE), min(H, band[1] * TILE)
+
+
+def gather_image_bands(img: torch.Tensor, bands: Sequence[Tuple[int, int]], group=None) -> torch.Tensor:
+    """``img`` is ``[C,H,W]`` with only this rank's band rows valid; returns the full ``[C,H,W]`` on every rank.
+
+    A single all-gather: each rank contributes its band packed into a ``[C, hmax, W]`` slab (bands may differ
+    in height by one tile row; shorter ones are zero padded)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    C, H, W = img.shape
+    rows = [band_pixel_rows(b, H) for b in bands]
+    hmax = max(r1 - r0 for r0, r1 in rows)
+    slab = torch.zeros((C, hmax, W), dtype=img.dtype, device=img.device)
+    r0, r1 = rows[rank]
+    slab[:, : r1 - r0] = img[:, r0:r1]
+    out = torch.empty((world, C, hmax, W), dtype=img.dtype, device=img.device)
+    try:
+        dist.all_gather_into_tensor(out, slab, group=group)
+    except (RuntimeError, NotImplementedError):        # backends without the fused form
+        parts = [torch.empty_like(slab) for _ in range(world)]
+        dist.all_gather(parts, slab, group=group)
+        out = torch.stack(parts)
+    full = torch.empty_like(img)
+    for r, (a, b) in enumerate(rows):
+        full[:, a:b] = out[r, :, : b - a]
+    return full
+
+
+def reduce_partials(accum: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the per-Gaussian partial-gradient arrays of all bands in place (all-reduce)."""
+    dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=group)
+    return accum
+
+
+class _ShardedRasterize(torch.autograd.Function):
+    """Tile-row sharded counterpart of ``diff_gaussian_rasterization._RasterizeGaussians``."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings, bands, group):
+        from diff_gaussian_rasterization import _C
+        s = raster_settings
+        rank = dist.get_rank(group)
+        args = (s.bg, means3D, colors_precomp, opacities, scales, rotations, s.scale_modifier, cov3Ds_precomp,
+                s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size, s.subpixel_offset,
+                s.image_height, s.image_width, sh, s.sh_degree, s.campos, s.prefiltered, s.debug)
+        prev = _C.get_tile_row_shard()
+        _C.set_tile_row_shard(*bands[rank])
+        try:
+            num_rendered, color, radii, geom, binning, img = _C.rasterize_gaussians(*args)
+        finally:
+            _C.set_tile_row_shard(*prev)
+        H, W = int(s.image_height), int(s.image_width)
+        offset = (128 - img.data_ptr()) % 128
+        final_T = img[offset:offset + 4 * H * W].view(torch.float32).view(1, H, W)
+        full = gather_image_bands(torch.cat([color, final_T], dim=0), bands, group)
+        ctx.raster_settings, ctx.num_rendered, ctx.bands, ctx.group = s, num_rendered, bands, group
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img)
+        accumulation = (1.0 - full[3]) if s.return_accumulation else None
+        return full[:3].contiguous(), radii, accumulation
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _1, _2):
+        from diff_gaussian_rasterization import _C
+        s = ctx.raster_settings
+        colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img = ctx.saved_tensors
+        args = (s.bg, means3D, radii, colors_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp,
+                s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size, s.subpixel_offset,
+                grad_out_color, sh, s.sh_degree, s.campos, geom, ctx.num_rendered, binning, img, s.debug)
+        rank = dist.get_rank(ctx.group)
+        prev = _C.get_tile_row_shard()
+        _C.set_tile_row_shard(*ctx.bands[rank])
+        try:
+            accum = _C.rasterize_gaussians_backward_partials(*args)
+            P = int(means3D.size(0))
+            reduce_partials(accum[: P * 12], ctx.group)
+            (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot) = \
+                _C.rasterize_gaussians_backward_finalize(accum, *args)
+        finally:
+            _C.set_tile_row_shard(*prev)
+        return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, None, None, None)
+
+
+class ShardedGaussianRasterizer(torch.nn.Module):
+    """Same call signature as ``GaussianRasterizer``; every rank must call it with identical arguments.
+    Returns the full image, radii and accumulation on every rank."""
+
+    def __init__(self, raster_settings, group=None, bands=None, row_weights=None):
+        super().__init__()
+        self.raster_settings = raster_settings
+        self.group = group
+        world = dist.get_world_size(group)
+        rows = (int(raster_settings.image_height) + TILE - 1) // TILE
+        self.bands = list(bands) if bands is not None else partition_tile_rows(rows, world, row_weights)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None) == (colors_precomp is None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        empty = torch.Tensor([])
+        return _ShardedRasterize.apply(
+            means3D, means2D, empty if shs is None else shs, empty if colors_precomp is None else colors_precomp,
+            opacities, empty if scales is None else scales, empty if rotations is None else rotations,
+            empty if cov3D_precomp is None else cov3D_precomp, self.raster_settings, self.bands, self.group)
