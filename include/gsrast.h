@@ -189,7 +189,8 @@ int gsr_img_views(const void* img_buffer, int W, int H,
 /* sorted (tile-major, depth-minor) Gaussian index list, R entries                          */
 int gsr_binning_views(const void* binning_buffer, int num_rendered, const uint32_t** point_list);
 /* per-Gaussian projected state: depths f32[P], packed records float4[2P]
- * {x, y, conic.x, conic.y | conic.z, opacity*coef, 0, 0}, tiles_touched u32[P], rgb f32[3P] */
+ * {x, y, hx, hy | conic.x, conic.y, conic.z, opacity*coef} (hx, hy: conservative half extents of the
+ * alpha >= 1/255 footprint, used for per-warp culling), tiles_touched u32[P], rgb f32[3P]            */
 int gsr_geom_views(const void* geom_buffer, int P, int M, const float** depths,
                    const float** records, const uint32_t** tiles_touched, const float** rgb);
 int gsr_get_stats(const void* geom_buffer, int P, int M, void* stream, GsrStats* out);

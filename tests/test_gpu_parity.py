@@ -59,7 +59,7 @@ def test_against_reference_golden(C, dev, name):
     rec = v["records"].cpu().numpy()
     assert np.array_equal(bits(v["depths"].cpu().numpy()[vis]), bits(gold["depths"][vis]))
     assert np.array_equal(bits(np.ascontiguousarray(rec[vis][:, 0:2])), bits(gold["means2D"][vis]))
-    assert np.array_equal(bits(np.ascontiguousarray(rec[vis][:, 2:6])), bits(gold["conic_opacity"][vis]))
+    assert np.array_equal(bits(np.ascontiguousarray(rec[vis][:, 4:8])), bits(gold["conic_opacity"][vis]))
     if "shs" in scene:
         assert np.array_equal(bits(v["rgb"].cpu().numpy()[vis]), bits(gold["rgb"][vis]))
     # pixels: tolerance 1e-4 (measured: identical bits)
@@ -107,7 +107,7 @@ def test_against_compiled_reference(C, dev, kw):
     vis = radii > 0
     assert torch.equal(v["depths"][vis].view(torch.int32), rv["depths"][vis].view(torch.int32))
     assert torch.equal(v["records"][vis][:, 0:2].contiguous().view(torch.int32), rv["means2D"][vis].view(torch.int32))
-    assert torch.equal(v["records"][vis][:, 2:6].contiguous().view(torch.int32),
+    assert torch.equal(v["records"][vis][:, 4:8].contiguous().view(torch.int32),
                        rv["conic_opacity"][vis].view(torch.int32))
     assert float((o["color"] - color).abs().max()) <= PIX_TOL
     for n in GRAD_NAMES:

@@ -80,7 +80,7 @@ def compare_case(name, kw, dev, with_oracle=True):
             a = vo["records"].cpu().numpy()[visn][:, 0:2]; b = vr["means2D"].cpu().numpy()[visn]
         else:
             rec = vo["records"].cpu().numpy()[visn]
-            a = np.ascontiguousarray(rec[:, [2, 3, 4, 5]]); b = vr["conic_opacity"].cpu().numpy()[visn]
+            a = np.ascontiguousarray(rec[:, [4, 5, 6, 7]]); b = vr["conic_opacity"].cpu().numpy()[visn]
         ok, ne = bits_equal(a, b)
         rep[ours_k + "_bits_ne"] = ne
         if ne:

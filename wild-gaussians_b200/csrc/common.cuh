@@ -40,7 +40,7 @@ struct TileRect { uint16_t x0, y0, x1, y1; };   // half-open tile rectangle of o
 
 struct GeomState {
     // persistent (read by the backward pass)
-    float4*   rec;            // [2P] {x, y, conic.x, conic.y | conic.z, opacity*coef, depth, 0}
+    float4*   rec;            // [2P] {x, y, hx, hy | conic.x, conic.y, conic.z, opacity*coef}
     float*    rgb;            // [3P] SH-evaluated colours (SH path only)
     uint8_t*  clamped;        // [P]  bit c set: channel c was clamped to 0 (SH path only)
     float*    depths;         // [P]  view-space z (exported for parity tests)

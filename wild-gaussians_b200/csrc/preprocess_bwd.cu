@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_consta
         // ---- 2D covariance / conic backward (backward.cu:144-310) ----
         const float3 dL_dconic = {o_conic[0], o_conic[1], o_conic[3]};
         const float4 rb = p.rec[2 * (size_t)idx + 1];
-        const float combined_opacity = rb.y;
+        const float combined_opacity = rb.w;
         const float h_x = p.focal_x, h_y = p.focal_y;
 
         const Ewa e = ewa_project(mean, h_x, h_y, p.tan_fovx, p.tan_fovy, cov3D, s_view);

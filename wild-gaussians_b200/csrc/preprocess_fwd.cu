@@ -7,8 +7,8 @@
 // computeColorFromSH (forward.cu:20-71), computeCov2D (:74-124), computeCov3D (:129-163),
 // in_frustum / ndc2Pix / getRect (auxiliary.h:41-56,139-164).  Differences in data layout,
 // not in arithmetic: the projected state is written as one 32-byte record per Gaussian
-// ({x, y, conic.x, conic.y | conic.z, opacity*coef, depth, 0}) so the compositing kernels
-// gather one aligned sector per instance; cov3D is not stored (the backward recomputes it);
+// ({x, y, hx, hy | conic.x, conic.y, conic.z, opacity*coef}; hx, hy = conservative half extents of
+// the alpha >= 1/255 footprint) so the compositing kernels gather one aligned sector per instance; cov3D is not stored (the backward recomputes it);
 // the tile rectangle is stored (8 B) so instance emission does not redo getRect; the depth
 // sort key is emitted here.
 #include "common.cuh"
@@ -191,8 +191,21 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         out_rect = {(uint16_t)rx0, (uint16_t)(rows ? cy0 : 0u), (uint16_t)rx1, (uint16_t)(rows ? cy1 : 0u)};
         out_key = __float_as_uint(p_view.z);
 
-        p.rec[2 * (size_t)idx + 0] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-        p.rec[2 * (size_t)idx + 1] = make_float4(conic.z, p.opacities[idx] * cov.w, p_view.z, 0.0f);
+        // Screen-space half extents of the region where this Gaussian can reach alpha >= 1/255
+        // (axis-aligned box of the ellipse d^T Sigma^-1 d <= 2 ln(255 o)), inflated by a safety margin
+        // far above fp32 rounding.  The compositing kernels use it to skip, per warp, Gaussians that
+        // cannot touch any of the warp's pixels; the skipped pairs are exactly pairs the reference
+        // rejects with its alpha < 1/255 test (forward.cu:365), so results are unchanged.
+        // Negative extents: opacity too low to ever pass the test.  NaNs fall through as "keep".
+        const float op = p.opacities[idx] * cov.w;
+        float hx = -1.f, hy = -1.f;
+        if (!(op < (1.0f / 255.0f) * 0.9999f)) {
+            const float tau = logf(255.0f * op) * 1.0001f + 1e-4f;
+            hx = sqrtf(2.f * tau * cov.x) * 1.0001f + 0.05f;
+            hy = sqrtf(2.f * tau * cov.z) * 1.0001f + 0.05f;
+        }
+        p.rec[2 * (size_t)idx + 0] = make_float4(point_image.x, point_image.y, hx, hy);
+        p.rec[2 * (size_t)idx + 1] = make_float4(conic.x, conic.y, conic.z, op);
         p.depths[idx] = p_view.z;
     } while (false);
 

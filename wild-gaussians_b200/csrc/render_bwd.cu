@@ -18,11 +18,11 @@
 //
 // The |grad| channel (backward.cu:593-595) is the sum over pixels of |gx| + |gy|, so the
 // absolute value is taken per lane BEFORE the warp reduction.
-#include "common.cuh"
+#include "render_common.cuh"
 
 namespace gsr {
 
-constexpr int RB_THREADS = 256;
+constexpr int RB_THREADS = RT_THREADS;
 constexpr int RB_ACC = 12;   // floats per Gaussian in the shared / global accumulator
 
 struct RenderBwdParams {
@@ -92,15 +92,18 @@ __device__ __forceinline__ int butterfly16(float (&v)[16], int lane) {
 
 __global__ void __launch_bounds__(RB_THREADS) render_bwd_kernel(const __grid_constant__ RenderBwdParams p) {
     __shared__ uint32_t s_id[RB_THREADS];
-    __shared__ __align__(16) float4 s_rec[RB_THREADS][2];
+    __shared__ __align__(16) float4 s_geo[RB_THREADS];   // {x, y, hx, hy}
+    __shared__ __align__(16) float4 s_con[RB_THREADS];   // {conic.x, conic.y, conic.z, opacity}
     __shared__ float s_col[RB_THREADS][3];
     __shared__ __align__(16) float s_acc[RB_THREADS][RB_ACC];
     __shared__ uint32_t s_max[RB_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + p.ty0;
-    const unsigned pix_x = tile_x * TILE + (tid & (TILE - 1));
-    const unsigned pix_y = tile_y * TILE + (tid >> 4);
+    int lx, ly;
+    tile_pixel(tid, lx, ly);
+    const unsigned pix_x = tile_x * TILE + lx;
+    const unsigned pix_y = tile_y * TILE + ly;
     const unsigned pix_id = p.W * pix_y + pix_x;
     const bool inside = pix_x < (unsigned)p.W && pix_y < (unsigned)p.H;
 
@@ -110,17 +113,18 @@ __global__ void __launch_bounds__(RB_THREADS) render_bwd_kernel(const __grid_con
         pixf.x += so.x;
         pixf.y += so.y;
     }
+    const WarpBox box = warp_box(pixf, inside);
     const uint2 range = p.ranges[tile_y * p.grid_x + tile_x];
 
     const float T_final = inside ? p.final_T[pix_id] : 0;
     float T = T_final;
     const uint32_t last_contributor = inside ? p.n_contrib[pix_id] : 0;
 
-    // tile-wide largest last_contributor: nothing behind it contributes to any pixel
-    uint32_t m = last_contributor;
+    // warp-wide and tile-wide largest last_contributor: nothing behind it contributes
+    uint32_t warp_last = last_contributor;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-    if (lane == 0) s_max[warp] = m;
+    for (int o = 16; o > 0; o >>= 1) warp_last = max(warp_last, __shfl_xor_sync(0xFFFFFFFFu, warp_last, o));
+    if (lane == 0) s_max[warp] = warp_last;
     __syncthreads();
     uint32_t tile_last = 0;
 #pragma unroll
@@ -143,7 +147,6 @@ __global__ void __launch_bounds__(RB_THREADS) render_bwd_kernel(const __grid_con
     const float ddelx_dx = 0.5 * p.W;
     const float ddely_dy = 0.5 * p.H;
 
-    uint32_t contributor = (uint32_t)total;   // ordinal (1-based) of the instance about to be visited
     int toDo = total;
     for (int r = 0; r < rounds; ++r, toDo -= RB_THREADS) {
         __syncthreads();   // previous round's accumulators flushed, staging buffers free
@@ -153,8 +156,8 @@ __global__ void __launch_bounds__(RB_THREADS) render_bwd_kernel(const __grid_con
                 const uint32_t id = p.point_list[range.x + total - progress - 1];
                 s_id[tid] = id;
                 const float4* src = p.rec + 2 * (size_t)id;
-                s_rec[tid][0] = src[0];
-                s_rec[tid][1] = src[1];
+                s_geo[tid] = src[0];
+                s_con[tid] = src[1];
                 s_col[tid][0] = p.colors[3 * (size_t)id + 0];
                 s_col[tid][1] = p.colors[3 * (size_t)id + 1];
                 s_col[tid][2] = p.colors[3 * (size_t)id + 2];
@@ -165,73 +168,98 @@ __global__ void __launch_bounds__(RB_THREADS) render_bwd_kernel(const __grid_con
         __syncthreads();
 
         const int n = min(RB_THREADS, toDo);
-        for (int j = 0; j < n; ++j) {
-            contributor--;
-            bool active = inside && contributor < last_contributor;
+        // 0-based list position of staged entry j: pos(j) = first_pos - j  (walking back to front)
+        const int first_pos = total - 1 - r * RB_THREADS;
 
-            const float4 ra = s_rec[j][0];
-            const float4 rb = s_rec[j][1];
-            const float2 xy = {ra.x, ra.y};
-            const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
-            const float4 con_o = {ra.z, ra.w, rb.x, rb.y};
-            const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-            if (power > 0.0f) active = false;
-            const float G = expf(power);
-            const float alpha = min(0.99f, con_o.w * G);
-            if (alpha < 1.0f / 255.0f) active = false;
-
-            if (!__any_sync(0xFFFFFFFFu, active)) continue;   // warp-uniform
-
-            float v[16];
+        // per-warp culling: staged Gaussians that are in front of this warp's deepest contributor and whose
+        // alpha >= 1/255 footprint can touch the warp's pixel block
+        unsigned mask[RB_THREADS / 32];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[k] = 0.f;
-            if (active) {
-                T = T / (1.f - alpha);
-                const float dchannel_dcolor = alpha * T;
-                float dL_dalpha = 0.0f;
+        for (int w = 0; w < RB_THREADS / 32; ++w) {
+            const int j = w * 32 + lane;
+            const bool rel = j < n && (uint32_t)(first_pos - j) < warp_last && box_may_touch(s_geo[j], box);
+            mask[w] = __ballot_sync(0xFFFFFFFFu, rel);
+        }
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float c = s_col[j][ch];
-                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-                    last_color[ch] = c;
-                    const float dL_dchannel = dL_dpixel[ch];
-                    dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
-                    v[7 + ch] = dchannel_dcolor * dL_dchannel;
+        for (int w = 0; w < RB_THREADS / 32; ++w) {
+            unsigned mm = mask[w];
+            while (mm) {
+                const int j = w * 32 + __ffs(mm) - 1;
+                mm &= mm - 1;
+                // the reference visits an instance iff its position is below the pixel's n_contrib
+                // (backward.cu:529-533)
+                bool active = inside && (uint32_t)(first_pos - j) < last_contributor;
+
+                const float4 geo = s_geo[j];
+                const float2 xy = {geo.x, geo.y};
+                const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
+                const float4 con_o = s_con[j];
+                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                if (power > 0.0f) active = false;
+                const float G = expf(power);
+                const float alpha = min(0.99f, con_o.w * G);
+                if (alpha < 1.0f / 255.0f) active = false;
+
+                if (!__any_sync(0xFFFFFFFFu, active)) continue;   // warp-uniform
+
+                float v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = 0.f;
+                if (active) {
+                    T = T / (1.f - alpha);
+                    const float dchannel_dcolor = alpha * T;
+                    float dL_dalpha = 0.0f;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float c = s_col[j][ch];
+                        accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                        last_color[ch] = c;
+                        const float dL_dchannel = dL_dpixel[ch];
+                        dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
+                        v[7 + ch] = dchannel_dcolor * dL_dchannel;
+                    }
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+
+                    float bg_dot_dpixel = 0;
+                    bg_dot_dpixel += bg0 * dL_dpixel[0];
+                    bg_dot_dpixel += bg1 * dL_dpixel[1];
+                    bg_dot_dpixel += bg2 * dL_dpixel[2];
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                    const float dL_dG = con_o.w * dL_dalpha;
+                    const float gdx = G * d.x;
+                    const float gdy = G * d.y;
+                    const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+                    const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+
+                    v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    v[1] = dL_dG * dG_ddely * ddely_dy;
+                    v[2] = fabsf(dL_dG * dG_ddelx * ddelx_dx) + fabsf(dL_dG * dG_ddely * ddely_dy);
+                    v[3] = -0.5f * gdx * d.x * dL_dG;
+                    v[4] = -0.5f * gdx * d.y * dL_dG;
+                    v[5] = -0.5f * gdy * d.y * dL_dG;
+                    v[6] = G * dL_dalpha;
                 }
-                dL_dalpha *= T;
-                last_alpha = alpha;
-
-                float bg_dot_dpixel = 0;
-                bg_dot_dpixel += bg0 * dL_dpixel[0];
-                bg_dot_dpixel += bg1 * dL_dpixel[1];
-                bg_dot_dpixel += bg2 * dL_dpixel[2];
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-
-                const float dL_dG = con_o.w * dL_dalpha;
-                const float gdx = G * d.x;
-                const float gdy = G * d.y;
-                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = fabsf(dL_dG * dG_ddelx * ddelx_dx) + fabsf(dL_dG * dG_ddely * ddely_dy);
-                v[3] = -0.5f * gdx * d.x * dL_dG;
-                v[4] = -0.5f * gdx * d.y * dL_dG;
-                v[5] = -0.5f * gdy * d.y * dL_dG;
-                v[6] = G * dL_dalpha;
+                const int slot = butterfly16(v, lane);
+                if ((lane & 1) == 0 && slot < 10) atomicAdd(&s_acc[j][slot], v[0]);
             }
-            const int slot = butterfly16(v, lane);
-            if ((lane & 1) == 0 && slot < 10) atomicAdd(&s_acc[j][slot], v[0]);
         }
         __syncthreads();
-        // one flush per visited Gaussian per tile: three 128-bit reductions
+        // one flush per visited Gaussian per tile: three 128-bit reductions (skipped when nothing landed)
         if (tid < n) {
-            float* dst = p.accum + (size_t)s_id[tid] * RB_ACC;
             const float* a = s_acc[tid];
-            red_add_v4(dst + 0, a[0], a[1], a[2], a[3]);
-            red_add_v4(dst + 4, a[4], a[5], a[6], a[7]);
-            red_add_v4(dst + 8, a[8], a[9], 0.f, 0.f);
+            const float4 a0 = *reinterpret_cast<const float4*>(a);
+            const float4 a1 = *reinterpret_cast<const float4*>(a + 4);
+            const float4 a2 = *reinterpret_cast<const float4*>(a + 8);
+            const bool any = (a0.x != 0.f) | (a0.y != 0.f) | (a0.z != 0.f) | (a0.w != 0.f) | (a1.x != 0.f) | (a1.y != 0.f) |
+                             (a1.z != 0.f) | (a1.w != 0.f) | (a2.x != 0.f) | (a2.y != 0.f);
+            if (any) {
+                float* dst = p.accum + (size_t)s_id[tid] * RB_ACC;
+                red_add_v4(dst + 0, a0.x, a0.y, a0.z, a0.w);
+                red_add_v4(dst + 4, a1.x, a1.y, a1.z, a1.w);
+                red_add_v4(dst + 8, a2.x, a2.y, 0.f, 0.f);
+            }
         }
     }
 }

@@ -1,22 +1,27 @@
 // render_fwd.cu -- per-tile front-to-back alpha compositing.
 // Replaces renderCUDA<3> of the reference (forward.cu:273-395).
 //
-// One CTA per 16x16 tile, one thread per pixel.  The tile's slice of the sorted instance list
-// is consumed in rounds of 256 instances; each round's 32-byte projected records and colours
-// are gathered into shared memory with asynchronous copies (cp.async / LDGSTS, no register
-// staging) into a double buffer, two rounds of Gaussian ids ahead, so the gather of round
-// r+1 overlaps the blending of round r.  Colours are staged too (the reference fetches them
-// from global memory inside the blend loop, forward.cu:376).
+// One CTA per 16x16 tile, one thread per pixel, each warp owning a compact 8x4 pixel block.  The tile's
+// slice of the sorted instance list is consumed in rounds of 256 instances; each round's 32-byte
+// projected records and colours are gathered into shared memory with asynchronous copies
+// (cp.async / LDGSTS, no register staging) into a double buffer, two rounds of Gaussian ids ahead, so
+// the gather of round r+1 overlaps the blending of round r.  Colours are staged too (the reference
+// fetches them from global memory inside the blend loop, forward.cu:376).
 //
-// Numerics contract (SURVEY.md 8a note N3): the expression shapes of power / alpha /
-// test_T / the colour accumulation are exactly the reference's (forward.cu:353-378,393), and
-// expf is the accurate one, so the three discontinuous tests (power > 0, alpha < 1/255,
-// T(1-alpha) < 1e-4) take the same branch and n_contrib / pixels match bit for bit.
-#include "common.cuh"
+// Per-warp culling: before blending a round, every lane tests 8 of the 256 staged Gaussians against the
+// bounding box of the warp's 32 sample positions using the conservative footprint extents computed
+// in preprocess_fwd.cu; eight ballots give the warp a 256-bit mask and only the set bits are blended.
+// The skipped (pixel, Gaussian) pairs are pairs the reference rejects with alpha < 1/255
+// (forward.cu:365), so the image, final_T and n_contrib are unchanged; `contributor` is derived from
+// the position in the list, not counted, so it still counts every instance like forward.cu:349.
+//
+// Numerics contract (SURVEY.md 8a note N3): the expression shapes of power / alpha / test_T / the
+// colour accumulation are exactly the reference's (forward.cu:353-378,393), and expf is the accurate
+// one, so the three discontinuous tests (power > 0, alpha < 1/255, T(1-alpha) < 1e-4) take the same
+// branch and n_contrib / pixels match bit for bit.
+#include "render_common.cuh"
 
 namespace gsr {
-
-constexpr int RF_THREADS = 256;
 
 struct RenderFwdParams {
     int W, H, grid_x, ty0;
@@ -31,28 +36,17 @@ struct RenderFwdParams {
     float* out_color;
 };
 
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
+__global__ void __launch_bounds__(RT_THREADS) render_fwd_kernel(const __grid_constant__ RenderFwdParams p) {
+    __shared__ __align__(16) float4 s_geo[2][RT_THREADS];   // {x, y, hx, hy}
+    __shared__ __align__(16) float4 s_con[2][RT_THREADS];   // {conic.x, conic.y, conic.z, opacity}
+    __shared__ float s_col[2][RT_THREADS][3];
 
-__global__ void __launch_bounds__(RF_THREADS) render_fwd_kernel(const __grid_constant__ RenderFwdParams p) {
-    __shared__ __align__(16) float4 s_rec[2][RF_THREADS][2];
-    __shared__ float s_col[2][RF_THREADS][3];
-
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + p.ty0;
-    const unsigned pix_x = tile_x * TILE + (tid & (TILE - 1));
-    const unsigned pix_y = tile_y * TILE + (tid >> 4);
+    int lx, ly;
+    tile_pixel(tid, lx, ly);
+    const unsigned pix_x = tile_x * TILE + lx;
+    const unsigned pix_y = tile_y * TILE + ly;
     const unsigned pix_id = p.W * pix_y + pix_x;
     const bool inside = pix_x < (unsigned)p.W && pix_y < (unsigned)p.H;
     bool done = !inside;
@@ -63,17 +57,18 @@ __global__ void __launch_bounds__(RF_THREADS) render_fwd_kernel(const __grid_con
         pixf.x += so.x;
         pixf.y += so.y;
     }
+    const WarpBox box = warp_box(pixf, inside);
 
     const uint2 range = p.ranges[tile_y * p.grid_x + tile_x];
     const int total = (int)(range.y - range.x);
-    const int rounds = (total + RF_THREADS - 1) / RF_THREADS;
+    const int rounds = (total + RT_THREADS - 1) / RT_THREADS;
 
     // gather of one round into buffer `buf`; `id` was loaded one iteration earlier
     auto stage = [&](int buf, int round, uint32_t id) {
-        if (round * RF_THREADS + tid < total) {
+        if (round * RT_THREADS + tid < total) {
             const float4* src = p.rec + 2 * (size_t)id;
-            cp_async_16(&s_rec[buf][tid][0], src);
-            cp_async_16(&s_rec[buf][tid][1], src + 1);
+            cp_async_16(&s_geo[buf][tid], src);
+            cp_async_16(&s_con[buf][tid], src + 1);
             const float* c = p.colors + 3 * (size_t)id;
             cp_async_4(&s_col[buf][tid][0], c);
             cp_async_4(&s_col[buf][tid][1], c + 1);
@@ -81,12 +76,11 @@ __global__ void __launch_bounds__(RF_THREADS) render_fwd_kernel(const __grid_con
         }
     };
     auto load_id = [&](int round) -> uint32_t {
-        const int i = round * RF_THREADS + tid;
+        const int i = round * RT_THREADS + tid;
         return (round < rounds && i < total) ? p.point_list[range.x + i] : 0u;
     };
 
     float T = 1.0f;
-    uint32_t contributor = 0;
     uint32_t last_contributor = 0;
     float C0 = 0.f, C1 = 0.f, C2 = 0.f;
 
@@ -97,13 +91,13 @@ __global__ void __launch_bounds__(RF_THREADS) render_fwd_kernel(const __grid_con
         id_next = load_id(1);
 
         int toDo = total;
-        for (int r = 0; r < rounds; ++r, toDo -= RF_THREADS) {
+        for (int r = 0; r < rounds; ++r, toDo -= RT_THREADS) {
             const int buf = r & 1;
             // this round's data has landed (for this thread) ...
             cp_async_wait<0>();
             // ... and for everyone; also the block-wide early-out vote (forward.cu:330-332)
             const int num_done = __syncthreads_count(done);
-            if (num_done == RF_THREADS) break;
+            if (num_done == RT_THREADS) break;
             // next round's gather overlaps this round's blending
             if (r + 1 < rounds) {
                 stage(buf ^ 1, r + 1, id_next);
@@ -111,29 +105,46 @@ __global__ void __launch_bounds__(RF_THREADS) render_fwd_kernel(const __grid_con
                 id_next = load_id(r + 2);
             }
 
-            const int n = min(RF_THREADS, toDo);
-            for (int j = 0; !done && j < n; ++j) {
-                contributor++;
-                const float4 ra = s_rec[buf][j][0];
-                const float4 rb = s_rec[buf][j][1];
-                const float2 xy = {ra.x, ra.y};
-                const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
-                const float4 con_o = {ra.z, ra.w, rb.x, rb.y};
-                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-                if (power > 0.0f) continue;
-
-                const float alpha = min(0.99f, con_o.w * expf(power));
-                if (alpha < 1.0f / 255.0f) continue;
-                const float test_T = T * (1 - alpha);
-                if (test_T < 0.0001f) {
-                    done = true;
-                    continue;
+            const int n = min(RT_THREADS, toDo);
+            const uint32_t round_base = (uint32_t)(r * RT_THREADS);
+            if (!__all_sync(0xFFFFFFFFu, done)) {
+                // which of the staged Gaussians can touch this warp's pixels?
+                unsigned mask[RT_THREADS / 32];
+#pragma unroll
+                for (int w = 0; w < RT_THREADS / 32; ++w) {
+                    const int j = w * 32 + lane;
+                    mask[w] = __ballot_sync(0xFFFFFFFFu, j < n && box_may_touch(s_geo[buf][j], box));
                 }
-                C0 += s_col[buf][j][0] * alpha * T;
-                C1 += s_col[buf][j][1] * alpha * T;
-                C2 += s_col[buf][j][2] * alpha * T;
-                T = test_T;
-                last_contributor = contributor;
+#pragma unroll
+                for (int w = 0; w < RT_THREADS / 32; ++w) {
+                    unsigned mm = mask[w];
+                    while (mm) {
+                        const int j = w * 32 + __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        if (done) continue;
+                        const float4 geo = s_geo[buf][j];
+                        const float2 xy = {geo.x, geo.y};
+                        const float2 d = {xy.x - pixf.x, xy.y - pixf.y};
+                        const float4 con_o = s_con[buf][j];
+                        const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+                        if (power > 0.0f) continue;
+
+                        const float alpha = min(0.99f, con_o.w * expf(power));
+                        if (alpha < 1.0f / 255.0f) continue;
+                        const float test_T = T * (1 - alpha);
+                        if (test_T < 0.0001f) {
+                            done = true;
+                            continue;
+                        }
+                        C0 += s_col[buf][j][0] * alpha * T;
+                        C1 += s_col[buf][j][1] * alpha * T;
+                        C2 += s_col[buf][j][2] * alpha * T;
+                        T = test_T;
+                        // 1-based position of this instance in the tile's list (forward.cu:349,382)
+                        last_contributor = round_base + (uint32_t)j + 1u;
+                    }
+                    if (__all_sync(0xFFFFFFFFu, done)) break;
+                }
             }
             // everyone is finished with `buf` before round r+2 is staged into it
             __syncthreads();
@@ -161,7 +172,7 @@ int launch_render_fwd(const GsrForwardArgs& a, const GeomState& g, const BinStat
     p.final_T = im.final_T; p.n_contrib = im.n_contrib; p.out_color = a.out_color;
     if (ty1 <= ty0) return 0;
     dim3 grid(p.grid_x, ty1 - ty0, 1);
-    render_fwd_kernel<<<grid, RF_THREADS, 0, s>>>(p);
+    render_fwd_kernel<<<grid, RT_THREADS, 0, s>>>(p);
     count_launches(1);
     return 0;
 }
