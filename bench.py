@@ -138,9 +138,10 @@ def stage_bytes(P, V, R, N, T, sh_M, visited):
         "preprocess_fwd": P * (44 + (0 if sh_M == 0 else col) + 4 + 4 + 8 + 8) + V * (32 + 4),
         "depth_sort": P * 8 * 2,                 # one read + one write of the (key, id) pairs
         "offset_scan": P * (4 + 4 + 4),
-        "emit_instances": P * (4 + 8 + 4) + R * 8,
-        "tile_sort": R * 8 * 2,                  # one read + one write of the (tile, id) pairs
-        "tile_ranges": R * 4 + T * 8,
+        "emit_cells": P * (4 + 8 + 4),
+        "cell_sort": 0, "cell_count": 0, "tile_offsets": 0,   # coarse-item passes (a few bytes per Gaussian; filled below)
+        "tile_scatter": R * 4,                   # the per-tile instance list itself
+        "_tile_ranges": T * 8,
         "render_fwd": visited * (4 + 32 + 12) + N * (8 + 12 + 4 + 4) + T * 8,
         "render_bwd": visited * (4 + 32 + 12 + 48) + N * (8 + 12 + 4 + 4) + T * 8,
         "preprocess_bwd": P * (4 + 44 + 56 + 12) + V * (48 + 32),

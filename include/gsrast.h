@@ -20,9 +20,9 @@
  * Buffer protocol (replaces the reference's three std::function<char*(size_t)> resize
  * callbacks, rasterize_points.cu:27-33,78-80):
  *   1. gsr_forward_sizes()     -> bytes for geom_buffer and img_buffer      (caller allocates)
- *   2. gsr_forward_geometry()  -> per-Gaussian projection, depth ordering, instance count R
+ *   2. gsr_forward_geometry()  -> per-Gaussian projection, depth ordering, instance counts
  *                                  (one stream sync, like rasterizer_impl.cu:283-284)
- *   3. gsr_binning_sizes(R)    -> bytes for binning_buffer and the transient scratch
+ *   3. gsr_binning_sizes()     -> bytes for binning_buffer and the transient scratch
  *   4. gsr_forward_render()    -> tile binning + per-tile front-to-back composite
  * gsr_forward() does 1-4 in one call through a C allocation callback.
  * geom/binning/img buffers must be kept (unmodified) for gsr_backward(); scratch may be
@@ -148,12 +148,16 @@ const char* gsr_last_error(void);
 
 /* -- forward ----------------------------------------------------------------------------- */
 int gsr_forward_sizes(int P, int M, int W, int H, size_t* geom_bytes, size_t* img_bytes);
+/* num_rendered = R, the number of (Gaussian, tile) instances (what the reference returns);
+ * num_coarse   = number of (Gaussian, 8x8-tile cell) items of the two-level binning: it sizes the
+ *                transient scratch and must be passed back to gsr_binning_sizes / gsr_forward_render. */
 int gsr_forward_geometry(const GsrForwardArgs* args, void* geom_buffer, void* img_buffer,
-                         void* stream, int* num_rendered);
-int gsr_binning_sizes(int P, int W, int H, int num_rendered,
+                         void* stream, int* num_rendered, int* num_coarse);
+int gsr_binning_sizes(int P, int W, int H, int num_rendered, int num_coarse,
                       size_t* binning_bytes, size_t* scratch_bytes);
 int gsr_forward_render(const GsrForwardArgs* args, void* geom_buffer, void* img_buffer,
-                       void* binning_buffer, void* scratch, int num_rendered, void* stream);
+                       void* binning_buffer, void* scratch, int num_rendered, int num_coarse,
+                       void* stream);
 int gsr_forward(const GsrForwardArgs* args, gsr_alloc_fn alloc, void* alloc_ctx,
                 void* stream, int* num_rendered);
 

@@ -46,10 +46,10 @@ def test_size_queries_need_no_gpu():
     g2 = c_size_t(0)
     assert lib.gsr_forward_sizes(1000, 16, 640, 480, byref(g2), byref(i)) == 0
     assert g2.value > g.value      # SH path keeps rgb + clamp flags
-    lib.gsr_binning_sizes.argtypes = [c_int, c_int, c_int, c_int, ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]
+    lib.gsr_binning_sizes.argtypes = [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_size_t), ctypes.POINTER(c_size_t)]
     b, s = c_size_t(0), c_size_t(0)
-    assert lib.gsr_binning_sizes(1000, 640, 480, 5000, byref(b), byref(s)) == 0
-    assert b.value >= 5000 * 8 and s.value >= 5000 * 8
+    assert lib.gsr_binning_sizes(1000, 640, 480, 5000, 1500, byref(b), byref(s)) == 0
+    assert b.value >= 5000 * 4 and s.value >= 1500 * 16
     lib.gsr_backward_scratch_bytes.restype = c_size_t
     assert lib.gsr_backward_scratch_bytes(1000) >= 48000
 
@@ -60,7 +60,8 @@ def test_invalid_arguments_are_rejected_with_a_message():
     a = C.GsrForwardArgs()
     a.P, a.W, a.H = 10, 64, 64            # required pointers left NULL
     R = c_int(0)
-    rc = lib.gsr_forward_geometry(byref(a), None, None, None, byref(R))
+    N1 = c_int(0)
+    rc = lib.gsr_forward_geometry(byref(a), None, None, None, byref(R), byref(N1))
     assert rc == -1
     assert b"NULL" in lib.gsr_last_error()
     assert lib.gsr_forward_sizes(-1, 0, 64, 64, None, None) == -1
@@ -69,4 +70,4 @@ def test_invalid_arguments_are_rejected_with_a_message():
     assert lib.gsr_backward(byref(b), None) == -1
     # P == 0 is legal and does nothing
     a0 = C.GsrForwardArgs(); a0.P, a0.W, a0.H = 0, 64, 64
-    assert lib.gsr_forward_geometry(byref(a0), None, None, None, byref(R)) == 0 and R.value == 0
+    assert lib.gsr_forward_geometry(byref(a0), None, None, None, byref(R), byref(N1)) == 0 and R.value == 0

@@ -30,11 +30,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 // ---- optional per-stage device timing (bench.py's roofline numbers come from here) -------------
 // Off by default.  When on, every stage is bracketed by two events on the caller's stream;
 // gsr_profile_read() synchronises nothing itself: the caller synchronises the stream first.
-enum Stage { ST_PREPROCESS_FWD = 0, ST_DEPTH_SORT, ST_OFFSET_SCAN, ST_EMIT, ST_TILE_SORT, ST_TILE_RANGES,
-             ST_RENDER_FWD, ST_RENDER_BWD, ST_PREPROCESS_BWD, ST_COUNT };
-static const char* const k_stage_names[ST_COUNT] = {"preprocess_fwd", "depth_sort", "offset_scan", "emit_instances",
-                                                    "tile_sort", "tile_ranges", "render_fwd", "render_bwd",
-                                                    "preprocess_bwd"};
+static const char* const k_stage_names[ST_COUNT] = {"preprocess_fwd", "depth_sort", "offset_scan", "emit_cells",
+                                                    "cell_sort", "cell_count", "tile_offsets", "tile_scatter",
+                                                    "render_fwd", "render_bwd", "preprocess_bwd"};
 static bool g_prof_on = false;
 static cudaEvent_t g_prof_ev[ST_COUNT][2];
 static bool g_prof_ev_ok = false;
@@ -43,7 +41,7 @@ static unsigned long long g_launches = 0;
 
 void count_launches(int n) { g_launches += (unsigned long long)n; }
 
-static void prof_begin(int st, cudaStream_t s) {
+void prof_begin(int st, cudaStream_t s) {
     if (!g_prof_on) return;
     if (!g_prof_ev_ok) {
         for (int i = 0; i < ST_COUNT; ++i) { cudaEventCreate(&g_prof_ev[i][0]); cudaEventCreate(&g_prof_ev[i][1]); }
@@ -51,7 +49,7 @@ static void prof_begin(int st, cudaStream_t s) {
     }
     cudaEventRecord(g_prof_ev[st][0], s);
 }
-static void prof_end(int st, cudaStream_t s) {
+void prof_end(int st, cudaStream_t s) {
     if (!g_prof_on) return;
     cudaEventRecord(g_prof_ev[st][1], s);
     g_prof_used[st] = true;
@@ -74,6 +72,7 @@ size_t carve_geom(char* base, int P, int M, GeomState* out) {
     take(cur, g.clamped, M > 0 ? n : 0);
     take(cur, g.depths, n);
     take(cur, g.tiles_touched, n);
+    take(cur, g.cells_touched, n);
     take(cur, g.rect, n);
     take(cur, g.counters, 8);
     take(cur, g.key_a, n);
@@ -104,26 +103,31 @@ size_t carve_bin(char* base, size_t R, BinState* out) {
     BinState b;
     char* cur = base;
     take(cur, b.point_list, R);
-    take(cur, b.tile_keys, R);
     if (out) *out = b;
     return (size_t)(cur - base) + 256;
 }
 
-size_t carve_bin_scratch(char* base, size_t R, BinScratch* out) {
+size_t carve_bin_scratch(char* base, size_t N1, int W, int H, BinScratch* out) {
     BinScratch b;
     char* cur = base;
-    take(cur, b.key, R);
-    take(cur, b.val, R);
-    b.radix_tmp_count = radix_tmp_elems(R);
-    take(cur, b.radix_tmp, b.radix_tmp_count);
+    const int gx = tiles_x(W), gy = tiles_y(H);
+    const size_t num_tiles = (size_t)gx * gy;
+    const size_t num_cells = (size_t)((gx + CELL - 1) / CELL) * ((gy + CELL - 1) / CELL);
+    take(cur, b.key_a, N1);
+    take(cur, b.val_a, N1);
+    take(cur, b.key_b, N1);
+    take(cur, b.val_b, N1);
+    take(cur, b.radix_tmp, radix_tmp_elems(N1));
+    take(cur, b.cell_range, num_cells);
+    take(cur, b.unit_base, num_cells + 1);
+    b.units_cap = ((N1 / UNIT + num_cells + 7) / 8) * 8;
+    take(cur, b.M, (size_t)CELL_TILES * b.units_cap);
+    take(cur, b.row_total, CELL_TILES);
+    take(cur, b.tile_count, num_tiles + 1);
+    take(cur, b.tile_start, num_tiles + 1);
+    take(cur, b.scan_tmp, scan_tmp_elems(num_tiles));
     if (out) *out = b;
     return (size_t)(cur - base) + 256;
-}
-
-static int num_bits(uint32_t n) {   // bits needed to represent values 0..n-1
-    int b = 0;
-    while (b < 32 && (1ull << b) < (unsigned long long)n) ++b;
-    return b;
 }
 
 static int check_fwd_args(const GsrForwardArgs* a) {
@@ -141,7 +145,11 @@ static int check_fwd_args(const GsrForwardArgs* a) {
         if (a->shs && (a->M <= 0 || !a->campos)) { set_error("shs given but M<=0 or campos NULL"); return GSR_E_INVALID; }
         if (a->shs && (a->D < 0 || a->D > 3 || (a->D + 1) * (a->D + 1) > a->M)) { set_error("SH degree %d does not fit M=%d", a->D, a->M); return GSR_E_INVALID; }
     }
-    if (tiles_x(a->W) > 65535 || tiles_y(a->H) > 65535) { set_error("image too large"); return GSR_E_INVALID; }
+    if (tiles_x(a->W) > 65535 || tiles_y(a->H) > 65535 ||
+        (size_t)((tiles_x(a->W) + CELL - 1) / CELL) * ((tiles_y(a->H) + CELL - 1) / CELL) > 65536) {
+        set_error("image too large");
+        return GSR_E_INVALID;
+    }
     return 0;
 }
 
@@ -188,20 +196,22 @@ int gsr_forward_sizes(int P, int M, int W, int H, size_t* geom_bytes, size_t* im
     return 0;
 }
 
-int gsr_binning_sizes(int P, int W, int H, int num_rendered, size_t* binning_bytes, size_t* scratch_bytes) {
-    (void)P; (void)W; (void)H;
-    if (num_rendered < 0) { set_error("bad num_rendered"); return GSR_E_INVALID; }
+int gsr_binning_sizes(int P, int W, int H, int num_rendered, int num_coarse, size_t* binning_bytes, size_t* scratch_bytes) {
+    (void)P;
+    if (num_rendered < 0 || num_coarse < 0 || W <= 0 || H <= 0) { set_error("bad sizes"); return GSR_E_INVALID; }
     if (binning_bytes) *binning_bytes = carve_bin(nullptr, (size_t)num_rendered, nullptr);
-    if (scratch_bytes) *scratch_bytes = carve_bin_scratch(nullptr, (size_t)num_rendered, nullptr);
+    if (scratch_bytes) *scratch_bytes = carve_bin_scratch(nullptr, (size_t)num_coarse, W, H, nullptr);
     return 0;
 }
 
-int gsr_forward_geometry(const GsrForwardArgs* a, void* geom_buffer, void* img_buffer, void* stream, int* num_rendered) {
+int gsr_forward_geometry(const GsrForwardArgs* a, void* geom_buffer, void* img_buffer, void* stream, int* num_rendered,
+                         int* num_coarse) {
     (void)img_buffer;
     int rc = check_fwd_args(a);
     if (rc) return rc;
-    if (!num_rendered) { set_error("num_rendered is NULL"); return GSR_E_INVALID; }
+    if (!num_rendered || !num_coarse) { set_error("num_rendered / num_coarse is NULL"); return GSR_E_INVALID; }
     *num_rendered = 0;
+    *num_coarse = 0;
     if (a->P == 0) return 0;
     if (!geom_buffer) { set_error("geom_buffer is NULL"); return GSR_E_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
@@ -225,30 +235,32 @@ int gsr_forward_geometry(const GsrForwardArgs* a, void* geom_buffer, void* img_b
     if (rc) return rc;
     prof_end(ST_DEPTH_SORT, s);
 
-    // instance offsets in depth order; offsets[P] = R
+    // coarse-item offsets in depth order; offsets[P] = number of coarse items
     prof_begin(ST_OFFSET_SCAN, s);
-    rc = scan_gathered(g.tiles_touched, g.order, g.offsets, (size_t)a->P, g.radix_tmp + radix_tmp_elems((size_t)a->P), s);
+    rc = scan_gathered(g.cells_touched, g.order, g.offsets, (size_t)a->P, g.radix_tmp + radix_tmp_elems((size_t)a->P), s);
     if (rc) return rc;
     GSR_STAGE(s, dbg, "scan_gathered");
     prof_end(ST_OFFSET_SCAN, s);
 
-    uint32_t R = 0;
+    uint32_t N1 = 0;
     int32_t counters[8];
-    GSR_CUDA(cudaMemcpyAsync(&R, g.offsets + a->P, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA(cudaMemcpyAsync(&N1, g.offsets + a->P, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     GSR_CUDA(cudaMemcpyAsync(counters, g.counters, sizeof(counters), cudaMemcpyDeviceToHost, s));
     GSR_CUDA(cudaStreamSynchronize(s));
     if (counters[0] != 0) {
         set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
         return GSR_E_PREFILTERED;
     }
-    if (R > 0x7FFFFFFFu) { set_error("instance count %u overflows int", R); return GSR_E_OVERFLOW; }
-    GSR_CUDA(cudaMemcpyAsync(g.counters + 2, &R, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    unsigned long long R = 0;
+    memcpy(&R, &counters[2], sizeof(R));
+    if (R > 0x7FFFFFFFull || N1 > 0x7FFFFFFFu) { set_error("instance count %llu overflows int", R); return GSR_E_OVERFLOW; }
     *num_rendered = (int)R;
+    *num_coarse = (int)N1;
     return 0;
 }
 
 int gsr_forward_render(const GsrForwardArgs* a, void* geom_buffer, void* img_buffer, void* binning_buffer, void* scratch,
-                       int num_rendered, void* stream) {
+                       int num_rendered, int num_coarse, void* stream) {
     int rc = check_fwd_args(a);
     if (rc) return rc;
     if (a->P == 0) return 0;
@@ -266,37 +278,12 @@ int gsr_forward_render(const GsrForwardArgs* a, void* geom_buffer, void* img_buf
     carve_img((char*)img_buffer, a->W, a->H, &im);
     const size_t R = (size_t)num_rendered;
     carve_bin((char*)binning_buffer, R, &b);
-    carve_bin_scratch((char*)scratch, R, &bs);
+    carve_bin_scratch((char*)scratch, (size_t)num_coarse, a->W, a->H, &bs);
     int ty0, ty1;
     shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
-    const int gx = tiles_x(a->W), gy = tiles_y(a->H);
-    const int num_tiles = gx * gy;
 
-    if (R > 0) {
-        // the partition ping-pongs A -> B -> A ...: emit into whichever side makes the last
-        // pass land in the persistent (tile_keys, point_list) pair
-        const int tile_bits = num_bits((uint32_t)num_tiles);
-        const bool even = (radix_num_passes(0, tile_bits) % 2) == 0;
-        uint32_t* ka = even ? b.tile_keys : bs.key;
-        uint32_t* va = even ? b.point_list : bs.val;
-        uint32_t* kb = even ? bs.key : b.tile_keys;
-        uint32_t* vb = even ? bs.val : b.point_list;
-        prof_begin(ST_EMIT, s);
-        rc = launch_emit_instances(g, a->P, gx, ka, va, s);
-        if (rc) return rc;
-        GSR_STAGE(s, dbg, "emit_instances_kernel");
-        prof_end(ST_EMIT, s);
-        // stable partition by tile id: the depth order inside each tile is preserved
-        prof_begin(ST_TILE_SORT, s);
-        rc = radix_sort_pairs(ka, va, kb, vb, R, 0, tile_bits, bs.radix_tmp, s, dbg);
-        if (rc) return rc;
-        prof_end(ST_TILE_SORT, s);
-    }
-    prof_begin(ST_TILE_RANGES, s);
-    rc = launch_tile_ranges(b.tile_keys, R, im.ranges, num_tiles, s);
+    rc = run_tile_binning(g, a->P, a->W, a->H, R, (size_t)num_coarse, bs, b.point_list, im.ranges, s, dbg);
     if (rc) return rc;
-    GSR_STAGE(s, dbg, "tile_ranges_kernel");
-    prof_end(ST_TILE_RANGES, s);
 
     const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
     prof_begin(ST_RENDER_FWD, s);
@@ -317,14 +304,15 @@ int gsr_forward(const GsrForwardArgs* a, gsr_alloc_fn alloc, void* ctx, void* st
     void* geom = alloc(ctx, GSR_BUF_GEOM, gb);
     void* img = alloc(ctx, GSR_BUF_IMG, ib);
     if (!geom || !img) { set_error("allocation callback returned NULL"); return GSR_E_INVALID; }
-    rc = gsr_forward_geometry(a, geom, img, stream, num_rendered);
+    int num_coarse = 0;
+    rc = gsr_forward_geometry(a, geom, img, stream, num_rendered, &num_coarse);
     if (rc) return rc;
-    rc = gsr_binning_sizes(a->P, a->W, a->H, *num_rendered, &bb, &sb);
+    rc = gsr_binning_sizes(a->P, a->W, a->H, *num_rendered, num_coarse, &bb, &sb);
     if (rc) return rc;
     void* bin = alloc(ctx, GSR_BUF_BINNING, bb);
     void* scr = alloc(ctx, GSR_BUF_SCRATCH, sb);
     if (!bin || !scr) { set_error("allocation callback returned NULL"); return GSR_E_INVALID; }
-    return gsr_forward_render(a, geom, img, bin, scr, *num_rendered, stream);
+    return gsr_forward_render(a, geom, img, bin, scr, *num_rendered, num_coarse, stream);
 }
 
 int gsr_forward_recolor(const GsrForwardArgs* a, const void* geom_buffer, const void* binning_buffer,
@@ -484,7 +472,7 @@ int gsr_get_stats(const void* geom_buffer, int P, int M, void* stream, GsrStats*
     GSR_CUDA(cudaMemcpyAsync(c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
     GSR_CUDA(cudaStreamSynchronize(s));
     out->num_visible = c[1];
-    out->num_rendered = c[2];
+    out->num_rendered = c[2];   // low word of the 64-bit instance counter
     out->num_tiles = 0;
     out->reserved = 0;
     return 0;

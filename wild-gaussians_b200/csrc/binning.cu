@@ -1,88 +1,320 @@
-// binning.cu -- (Gaussian, tile) instance emission in depth order and per-tile range
-// detection.  Replaces duplicateWithKeys (rasterizer_impl.cu:70-111) and identifyTileRanges
-// (:116-138) of the reference.
+// binning.cu -- two-level stable tile binning: from the depth-ordered Gaussians to the per-tile,
+// front-to-back instance lists (point_list) and tile ranges.  Replaces duplicateWithKeys
+// (rasterizer_impl.cu:70-111), the 64-bit radix sort (:303-311) and identifyTileRanges (:116-138,313-320).
 //
-// The reference emits one 64-bit key (tile << 32 | depth bits) + 32-bit value per instance
-// in Gaussian-index order and radix-sorts all R of them over 41-48 key bits (6 passes, about
-// 150 B of HBM traffic per instance).  Here the Gaussians were already ordered by depth
-// (4 radix passes over P, not R, pairs), so instances are emitted front-to-back and only
-// have to be stably partitioned by their 32-bit tile id (2 radix passes).  The final order
-// (tile-major, depth-minor, ties by Gaussian index) is identical -- a stable sort is unique.
+// The reference materialises R = sum(tiles touched) 96-bit (key, value) pairs and radix-sorts them over
+// 41-48 key bits: about 150 bytes of HBM traffic per instance.  The result it needs is much smaller:
+// for every tile, the ids of the Gaussians overlapping it, front to back.  Because the Gaussians are
+// already in depth order (4 radix passes over P pairs, radix.cu), that list is a *stable partition* of
+// the depth-ordered instance stream by tile id, and a stable partition can be built hierarchically
+// without ever writing a key per instance:
 //
-// Emission is warp-cooperative: the 32 Gaussians of a warp are expanded by all 32 lanes
-// together, so a splat covering 1000 tiles costs 32 coalesced iterations instead of one
-// thread's 1000-iteration loop (the load imbalance noted in SURVEY.md 8a row a9).
+//   level 1  the screen is cut into cells of 8x8 tiles.  Each Gaussian emits one 8-byte coarse item per
+//            cell its tile rectangle overlaps (about 2 per Gaussian instead of about 13 tile instances),
+//            carrying the cell id and the rectangle clipped to the cell; a stable radix sort on the
+//            cell id groups them by cell, depth order preserved inside each cell.
+//   level 2  every cell's list is cut into units of 256 coarse items, one warp per unit.  A counting
+//            kernel histograms each unit over the cell's 64 tiles; a row scan turns the counts into the
+//            exact output position of every (unit, tile); the scatter kernel then walks each unit in
+//            order, 32 items at a time, and for every tile of the cell uses one ballot to rank the lanes
+//            covering it -- consecutive covering lanes write consecutive 4-byte slots of that tile's list.
+//
+// The order inside a tile is the order of the coarse items in the cell = depth order, ties by Gaussian
+// index (the depth sort is stable) -- exactly the reference's (tile | depth) stable sort (SURVEY.md note
+// N4).  Traffic is about 4 bytes per instance (the list itself) plus a few tens of bytes per Gaussian.
+// No spin-waits anywhere: every kernel is a plain data-parallel launch.
 #include "common.cuh"
 
 namespace gsr {
 
-__global__ void __launch_bounds__(256) emit_instances_kernel(int P, int grid_x, const uint32_t* __restrict__ order,
-                                                             const uint32_t* __restrict__ offsets,
-                                                             const TileRect* __restrict__ rect,
-                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// ---- level 1: coarse items ------------------------------------------------------------------------
+// key = cell id (low 16 bits) | x0 << 16 | y0 << 20 | x1 << 24 | y1 << 28, rectangle local to the cell
+__global__ void __launch_bounds__(256) emit_cells_kernel(int P, int cells_x, const uint32_t* __restrict__ order,
+                                                         const uint32_t* __restrict__ offsets,
+                                                         const TileRect* __restrict__ rect,
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // position in depth order
-    const int lane = threadIdx.x & 31;
-    uint32_t g = 0, off = 0, x0 = 0, y0 = 0, w = 0, cnt = 0;
-    if (i < P) {
-        g = order[i];
-        const TileRect r = rect[g];
-        w = (uint32_t)r.x1 - r.x0;
-        cnt = w * ((uint32_t)r.y1 - r.y0);
-        x0 = r.x0;
-        y0 = r.y0;
-        off = offsets[i];
-    }
-    const unsigned have = __ballot_sync(0xFFFFFFFFu, cnt != 0);
-    unsigned todo = have;
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t sg = __shfl_sync(0xFFFFFFFFu, g, src);
-        const uint32_t so = __shfl_sync(0xFFFFFFFFu, off, src);
-        const uint32_t sx = __shfl_sync(0xFFFFFFFFu, x0, src);
-        const uint32_t sy = __shfl_sync(0xFFFFFFFFu, y0, src);
-        const uint32_t sw = __shfl_sync(0xFFFFFFFFu, w, src);
-        const uint32_t sc = __shfl_sync(0xFFFFFFFFu, cnt, src);
-        // instance k of this Gaussian covers tile (sy + k / sw, sx + k % sw): row-major over
-        // the rectangle, the emission order of the reference (rasterizer_impl.cu:96-108)
-        for (uint32_t k = lane; k < sc; k += 32) {
-            const uint32_t ry = k / sw, rx = k - ry * sw;
-            keys[so + k] = (sy + ry) * (uint32_t)grid_x + (sx + rx);
-            vals[so + k] = sg;
+    if (i >= P) return;
+    const uint32_t g = order[i];
+    const TileRect r = rect[g];
+    if (r.x1 <= r.x0 || r.y1 <= r.y0) return;
+    uint32_t off = offsets[i];
+    const int cx0 = r.x0 / CELL, cx1 = (r.x1 - 1) / CELL + 1;
+    const int cy0 = r.y0 / CELL, cy1 = (r.y1 - 1) / CELL + 1;
+    for (int cy = cy0; cy < cy1; ++cy) {
+        const uint32_t ly0 = (uint32_t)max((int)r.y0 - cy * CELL, 0), ly1 = (uint32_t)min((int)r.y1 - cy * CELL, CELL);
+        for (int cx = cx0; cx < cx1; ++cx) {
+            const uint32_t lx0 = (uint32_t)max((int)r.x0 - cx * CELL, 0), lx1 = (uint32_t)min((int)r.x1 - cx * CELL, CELL);
+            keys[off] = (uint32_t)(cy * cells_x + cx) | (lx0 << 16) | (ly0 << 20) | (lx1 << 24) | (ly1 << 28);
+            vals[off] = g;
+            ++off;
         }
     }
 }
 
-int launch_emit_instances(const GeomState& g, int P, int gx, uint32_t* keys, uint32_t* vals, cudaStream_t s) {
-    if (P == 0) return 0;
-    emit_instances_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, gx, g.order, g.offsets, g.rect, keys, vals);
-    count_launches(1);
-    return 0;
-}
-
-// ranges[t] = [first, last+1) of tile t in the sorted instance list; empty tiles keep (0,0)
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ tile_keys, size_t R,
-                                                          uint2* __restrict__ ranges) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t cur = tile_keys[i];
+// cell_range[c] = [first, end) of cell c in the sorted coarse list; empty cells keep (0, 0)
+__global__ void __launch_bounds__(256) cell_bounds_kernel(const uint32_t* __restrict__ keys, uint32_t n1,
+                                                          uint2* __restrict__ cell_range) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    const uint32_t c = keys[i] & 0xFFFFu;
     if (i == 0) {
-        ranges[cur].x = 0;
+        cell_range[c].x = 0;
     } else {
-        const uint32_t prev = tile_keys[i - 1];
-        if (cur != prev) {
-            ranges[prev].y = (uint32_t)i;
-            ranges[cur].x = (uint32_t)i;
+        const uint32_t prev = keys[i - 1] & 0xFFFFu;
+        if (prev != c) {
+            cell_range[prev].y = i;
+            cell_range[c].x = i;
         }
     }
-    if (i == R - 1) ranges[cur].y = (uint32_t)R;
+    if (i == n1 - 1) cell_range[c].y = n1;
 }
 
-int launch_tile_ranges(const uint32_t* sorted_tile_keys, size_t R, uint2* ranges, int num_tiles, cudaStream_t s) {
-    GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
-    if (R == 0) return 0;
-    tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(sorted_tile_keys, R, ranges);
+// One CTA: units per cell (ceil(len / UNIT)) and their exclusive scan unit_base[0..NC];
+// unit_base[NC] = number of units.
+__global__ void __launch_bounds__(1024) build_units_kernel(const uint2* __restrict__ cell_range, uint32_t num_cells,
+                                                           uint32_t* __restrict__ unit_base) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < num_cells; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = 0;
+        if (i < num_cells) {
+            const uint2 cr = cell_range[i];
+            v = (cr.y - cr.x + UNIT - 1) / UNIT;
+        }
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t warp_excl = warp == 0 ? 0u : s_warp[warp - 1];
+        const uint32_t carry = s_carry;
+        if (i < num_cells) unit_base[i] = carry + warp_excl + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) unit_base[num_cells] = s_carry;
+}
+
+// unit u belongs to the cell c with unit_base[c] <= u < unit_base[c+1]
+__device__ __forceinline__ uint32_t cell_of_unit(const uint32_t* __restrict__ unit_base, uint32_t num_cells, uint32_t u) {
+    uint32_t lo = 0, hi = num_cells;   // invariant: unit_base[lo] <= u < unit_base[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (unit_base[mid] <= u) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+struct UnitInfo {
+    uint32_t cell, first, count, first_unit_of_cell;
+};
+__device__ __forceinline__ UnitInfo unit_info(const uint32_t* __restrict__ unit_base, const uint2* __restrict__ cell_range,
+                                              uint32_t num_cells, uint32_t u) {
+    UnitInfo ui;
+    ui.cell = cell_of_unit(unit_base, num_cells, u);
+    ui.first_unit_of_cell = unit_base[ui.cell];
+    const uint2 cr = cell_range[ui.cell];
+    ui.first = cr.x + (u - ui.first_unit_of_cell) * UNIT;
+    ui.count = min((uint32_t)UNIT, cr.y - ui.first);
+    return ui;
+}
+
+// ---- level 2a: per-(unit, local tile) counts, tile-major: M[t][u] -----------------------------------
+__global__ void __launch_bounds__(256) cell_count_kernel(const uint32_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ unit_base,
+                                                         const uint2* __restrict__ cell_range, uint32_t num_cells,
+                                                         uint32_t cap, uint32_t* __restrict__ M) {
+    __shared__ uint32_t s_cnt[8][CELL_TILES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t u = blockIdx.x * 8 + warp;
+    if (u >= cap) return;
+    const uint32_t num_units = unit_base[num_cells];
+    s_cnt[warp][lane] = 0;
+    s_cnt[warp][lane + 32] = 0;
+    __syncwarp();
+    if (u < num_units) {
+        const UnitInfo ui = unit_info(unit_base, cell_range, num_cells, u);
+        for (uint32_t k = lane; k < ui.count; k += 32) {
+            const uint32_t key = keys[ui.first + k];
+            const uint32_t x0 = (key >> 16) & 15u, y0 = (key >> 20) & 15u, x1 = (key >> 24) & 15u, y1 = (key >> 28) & 15u;
+            for (uint32_t y = y0; y < y1; ++y)
+                for (uint32_t x = x0; x < x1; ++x) atomicAdd(&s_cnt[warp][y * CELL + x], 1u);
+        }
+        __syncwarp();
+    }
+    // units beyond num_units (capacity padding) get zero rows so the row scan is well defined
+    M[(size_t)lane * cap + u] = s_cnt[warp][lane];
+    M[(size_t)(lane + 32) * cap + u] = s_cnt[warp][lane + 32];
+}
+
+// ---- level 2b: per-tile totals in global tile order --------------------------------------------------
+// After the row scan, Pm[t][u] = sum of M[t][u'] for u' < u (over all cells), row_total[t] = Pm[t][cap].
+__device__ __forceinline__ uint32_t prefix_at(const uint32_t* __restrict__ Pm, const uint32_t* __restrict__ row_total,
+                                              uint32_t cap, uint32_t t, uint32_t u) {
+    return u >= cap ? row_total[t] : Pm[(size_t)t * cap + u];
+}
+
+__global__ void __launch_bounds__(256) tile_counts_kernel(const uint32_t* __restrict__ Pm, const uint32_t* __restrict__ row_total,
+                                                          const uint32_t* __restrict__ unit_base, uint32_t num_cells,
+                                                          uint32_t cap, int cells_x, int grid_x, int grid_y,
+                                                          uint32_t* __restrict__ tile_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // (cell, local tile)
+    if (i >= num_cells * CELL_TILES) return;
+    const uint32_t c = i / CELL_TILES, t = i % CELL_TILES;
+    const int tx = (int)(c % cells_x) * CELL + (int)(t % CELL), ty = (int)(c / cells_x) * CELL + (int)(t / CELL);
+    if (tx >= grid_x || ty >= grid_y) return;
+    const uint32_t a = prefix_at(Pm, row_total, cap, t, unit_base[c]);
+    const uint32_t b = prefix_at(Pm, row_total, cap, t, unit_base[c + 1]);
+    tile_count[ty * grid_x + tx] = b - a;
+}
+
+// ranges[t] = [start, start + count); empty tiles are (0, 0) like the reference (rasterizer_impl.cu:313)
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ tile_start,
+                                                          const uint32_t* __restrict__ tile_count, int num_tiles,
+                                                          uint2* __restrict__ ranges) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    const uint32_t c = tile_count[t], s = tile_start[t];
+    ranges[t] = c ? make_uint2(s, s + c) : make_uint2(0u, 0u);
+}
+
+// ---- level 2c: scatter ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cell_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                           const uint32_t* __restrict__ unit_base,
+                                                           const uint2* __restrict__ cell_range, uint32_t num_cells,
+                                                           const uint32_t* __restrict__ Pm, const uint32_t* __restrict__ row_total,
+                                                           uint32_t cap, const uint32_t* __restrict__ tile_start, int cells_x,
+                                                           int grid_x, int grid_y, uint32_t* __restrict__ point_list) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t u = blockIdx.x * 8 + warp;
+    const uint32_t num_units = unit_base[num_cells];
+    if (u >= num_units) return;
+    const UnitInfo ui = unit_info(unit_base, cell_range, num_cells, u);
+    // running output position of local tiles `lane` (pos[0]) and `lane + 32` (pos[1])
+    uint32_t pos[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t t = lane + 32 * h;
+        const int tx = (int)(ui.cell % cells_x) * CELL + (int)(t % CELL), ty = (int)(ui.cell / cells_x) * CELL + (int)(t / CELL);
+        uint32_t p = 0;
+        if (tx < grid_x && ty < grid_y)
+            p = tile_start[ty * grid_x + tx] + prefix_at(Pm, row_total, cap, t, u) -
+                prefix_at(Pm, row_total, cap, t, ui.first_unit_of_cell);
+        pos[h] = p;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < ui.count; base += 32) {
+        const bool valid = base + lane < ui.count;
+        uint32_t key = 0, id = 0;
+        if (valid) {
+            key = keys[ui.first + base + lane];
+            id = vals[ui.first + base + lane];
+        }
+        const int x0 = (key >> 16) & 15, y0 = (key >> 20) & 15;
+        const int x1 = valid ? (key >> 24) & 15 : 0, y1 = valid ? (key >> 28) & 15 : 0;
+        // rows of the cell touched by any of the 32 items
+        const int ymin = __reduce_min_sync(0xFFFFFFFFu, valid ? y0 : CELL);
+        const int ymax = __reduce_max_sync(0xFFFFFFFFu, y1);
+        for (int y = ymin; y < ymax; ++y) {
+            const bool in_row = y >= y0 && y < y1;
+#pragma unroll
+            for (int x = 0; x < CELL; ++x) {
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, in_row && x >= x0 && x < x1);
+                if (m == 0) continue;
+                const int t = y * CELL + x;
+                const uint32_t b = __shfl_sync(0xFFFFFFFFu, (t & 32) ? pos[1] : pos[0], t & 31);
+                if (m & (1u << lane)) point_list[b + __popc(m & lt)] = id;
+                if (lane == (t & 31)) pos[t >> 5] += __popc(m);
+            }
+        }
+    }
+}
+
+// ---- orchestration -----------------------------------------------------------------------------------
+int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R, size_t N1, const BinScratch& bs,
+                     uint32_t* point_list, uint2* ranges, cudaStream_t s, bool debug) {
+    const int gx = tiles_x(W), gy = tiles_y(H);
+    const int cells_x = (gx + CELL - 1) / CELL, cells_y = (gy + CELL - 1) / CELL;
+    const uint32_t num_cells = (uint32_t)(cells_x * cells_y);
+    const int num_tiles = gx * gy;
+    if (N1 == 0 || R == 0) {
+        GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
+        return 0;
+    }
+    // level 1: emit + stable sort by cell id; the sorted result must land in (key_b, val_b)
+    prof_begin(ST_EMIT_CELLS, s);
+    int cell_bits = 0;
+    while ((1u << cell_bits) < num_cells) ++cell_bits;
+    const bool even = (radix_num_passes(0, cell_bits) % 2) == 0;
+    uint32_t* ka = even ? bs.key_b : bs.key_a;
+    uint32_t* va = even ? bs.val_b : bs.val_a;
+    uint32_t* kb = even ? bs.key_a : bs.key_b;
+    uint32_t* vb = even ? bs.val_a : bs.val_b;
+    emit_cells_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, cells_x, g.order, g.offsets, g.rect, ka, va);
     count_launches(1);
+    GSR_STAGE(s, debug, "emit_cells_kernel");
+    prof_end(ST_EMIT_CELLS, s);
+    prof_begin(ST_CELL_SORT, s);
+    int rc = radix_sort_pairs(ka, va, kb, vb, N1, 0, cell_bits, bs.radix_tmp, s, debug);
+    if (rc) return rc;
+    const uint32_t* keys = bs.key_b;
+    const uint32_t* vals = bs.val_b;
+    prof_end(ST_CELL_SORT, s);
+    prof_begin(ST_CELL_COUNT, s);
+
+    // units + per-unit tile counts
+    const uint32_t cap = (uint32_t)bs.units_cap;
+    GSR_CUDA(cudaMemsetAsync(bs.cell_range, 0, (size_t)num_cells * sizeof(uint2), s));
+    cell_bounds_kernel<<<(unsigned)((N1 + 255) / 256), 256, 0, s>>>(keys, (uint32_t)N1, bs.cell_range);
+    count_launches(1);
+    build_units_kernel<<<1, 1024, 0, s>>>(bs.cell_range, num_cells, bs.unit_base);
+    count_launches(1);
+    GSR_STAGE(s, debug, "build_units_kernel");
+    cell_count_kernel<<<(cap + 7) / 8, 256, 0, s>>>(keys, bs.unit_base, bs.cell_range, num_cells, cap, bs.M);
+    count_launches(1);
+    GSR_STAGE(s, debug, "cell_count_kernel");
+    prof_end(ST_CELL_COUNT, s);
+    prof_begin(ST_TILE_OFFSETS, s);
+
+    // exact output positions
+    rc = row_scan_u32(bs.M, CELL_TILES, cap, bs.row_total, s);
+    if (rc) return rc;
+    GSR_CUDA(cudaMemsetAsync(bs.tile_count, 0, ((size_t)num_tiles + 1) * sizeof(uint32_t), s));
+    tile_counts_kernel<<<(num_cells * CELL_TILES + 255) / 256, 256, 0, s>>>(bs.M, bs.row_total, bs.unit_base, num_cells, cap,
+                                                                         cells_x, gx, gy, bs.tile_count);
+    count_launches(1);
+    rc = scan_gathered(bs.tile_count, nullptr, bs.tile_start, (size_t)num_tiles, bs.scan_tmp, s);
+    if (rc) return rc;
+    tile_ranges_kernel<<<(num_tiles + 255) / 256, 256, 0, s>>>(bs.tile_start, bs.tile_count, num_tiles, ranges);
+    count_launches(1);
+    GSR_STAGE(s, debug, "tile_ranges_kernel");
+    prof_end(ST_TILE_OFFSETS, s);
+    prof_begin(ST_TILE_SCATTER, s);
+
+    cell_scatter_kernel<<<(cap + 7) / 8, 256, 0, s>>>(keys, vals, bs.unit_base, bs.cell_range, num_cells, bs.M, bs.row_total,
+                                                      cap, bs.tile_start, cells_x, gx, gy, point_list);
+    count_launches(1);
+    GSR_STAGE(s, debug, "cell_scatter_kernel");
+    prof_end(ST_TILE_SCATTER, s);
     return 0;
 }
 

@@ -10,6 +10,9 @@ namespace gsr {
 
 constexpr int TILE = 16;              // tile edge in pixels (reference config.h:16-17)
 constexpr int TILE_PIX = TILE * TILE;
+constexpr int CELL = 8;               // binning cell edge in tiles (binning.cu)
+constexpr int CELL_TILES = CELL * CELL;
+constexpr int UNIT = 256;             // coarse items per binning unit (one warp)
 constexpr float NEAR_Z = 0.2f;        // near cull (reference auxiliary.h:154)
 
 // ----------------------------------------------------------------------------------------
@@ -17,6 +20,12 @@ constexpr float NEAR_Z = 0.2f;        // near cull (reference auxiliary.h:154)
 // ----------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 void count_launches(int n);   // kernels launched by this library (bench.py's gpu_launches)
+
+// optional per-stage device timing (api.cu); no-ops unless gsr_profile_enable(1)
+enum Stage { ST_PREPROCESS_FWD = 0, ST_DEPTH_SORT, ST_OFFSET_SCAN, ST_EMIT_CELLS, ST_CELL_SORT, ST_CELL_COUNT,
+             ST_TILE_OFFSETS, ST_TILE_SCATTER, ST_RENDER_FWD, ST_RENDER_BWD, ST_PREPROCESS_BWD, ST_COUNT };
+void prof_begin(int stage, cudaStream_t s);
+void prof_end(int stage, cudaStream_t s);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define GSR_CUDA(expr)                                                        \
@@ -45,15 +54,16 @@ struct GeomState {
     uint8_t*  clamped;        // [P]  bit c set: channel c was clamped to 0 (SH path only)
     float*    depths;         // [P]  view-space z (exported for parity tests)
     uint32_t* tiles_touched;  // [P]
+    uint32_t* cells_touched;  // [P]  binning cells (8x8 tiles) overlapped by the tile rectangle
     TileRect* rect;           // [P]
-    int32_t*  counters;       // [8]  0: prefiltered violation, 1: visible count, 2: R
+    int32_t*  counters;       // [8]  0: prefiltered violation, 1: visible count, 2-3: R (u64), 4: coarse items
     // transient (depth ordering + instance offsets)
     uint32_t* key_a;          // [P]
     uint32_t* key_b;          // [P]
     uint32_t* val_a;          // [P]
     uint32_t* val_b;          // [P]
     uint32_t* order;          // alias of val_a: after the 4-pass depth sort, Gaussian ids front to back
-    uint32_t* offsets;        // [P+1] exclusive scan of tiles_touched in depth order
+    uint32_t* offsets;        // [P+1] exclusive scan of cells_touched in depth order
     uint32_t* radix_tmp;      // histogram / scan temporaries
     size_t    radix_tmp_count;
 };
@@ -66,20 +76,28 @@ struct ImgState {
 
 struct BinState {
     uint32_t* point_list;     // [R] sorted Gaussian ids (tile-major, depth-minor)
-    uint32_t* tile_keys;      // [R] sorted tile ids
 };
 
-struct BinScratch {
-    uint32_t* key;            // [R]
-    uint32_t* val;            // [R]
+struct BinScratch {           // transient state of the two-level tile binning (binning.cu)
+    uint32_t* key_a;          // [N1] coarse items: cell id | local rect
+    uint32_t* val_a;          // [N1] Gaussian ids
+    uint32_t* key_b;          // [N1]
+    uint32_t* val_b;          // [N1]
     uint32_t* radix_tmp;
-    size_t    radix_tmp_count;
+    uint2*    cell_range;     // [NC]
+    uint32_t* unit_base;      // [NC+1]
+    size_t    units_cap;      // upper bound of the number of units: N1 / UNIT + NC, rounded up to 8
+    uint32_t* M;              // [64][units_cap] per-(local tile, unit) counts, then their row-wise prefix
+    uint32_t* row_total;      // [64]
+    uint32_t* tile_count;     // [T+1]
+    uint32_t* tile_start;     // [T+1]
+    uint32_t* scan_tmp;
 };
 
 size_t carve_geom(char* base, int P, int M, GeomState* out);       // returns bytes used
 size_t carve_img(char* base, int W, int H, ImgState* out);
 size_t carve_bin(char* base, size_t R, BinState* out);
-size_t carve_bin_scratch(char* base, size_t R, BinScratch* out);
+size_t carve_bin_scratch(char* base, size_t N1, int W, int H, BinScratch* out);
 
 inline int tiles_x(int W) { return (W + TILE - 1) / TILE; }
 inline int tiles_y(int H) { return (H + TILE - 1) / TILE; }
@@ -100,8 +118,11 @@ int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, s
                   uint32_t* tmp, cudaStream_t s);
 size_t scan_tmp_elems(size_t n);
 
-int launch_emit_instances(const GeomState& g, int P, int gx, uint32_t* keys, uint32_t* vals, cudaStream_t s);
-int launch_tile_ranges(const uint32_t* sorted_tile_keys, size_t R, uint2* ranges, int num_tiles, cudaStream_t s);
+// in-place exclusive scan along each row of a [rows][cols] u32 matrix; row sums -> total[rows]
+int row_scan_u32(uint32_t* m, int rows, size_t cols, uint32_t* total, cudaStream_t s);
+// per-tile instance lists + ranges from the depth-ordered Gaussians (binning.cu)
+int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R, size_t N1, const BinScratch& bs,
+                     uint32_t* point_list, uint2* ranges, cudaStream_t s, bool debug);
 
 int launch_render_fwd(const GsrForwardArgs& a, const GeomState& g, const BinState& b, const ImgState& im,
                       const float* colors, int ty0, int ty1, cudaStream_t s);

@@ -39,6 +39,7 @@ struct PreFwdParams {
     uint8_t* clamped;
     float* depths;
     uint32_t* tiles_touched;
+    uint32_t* cells_touched;
     TileRect* rect;
     uint32_t* sort_key;
     uint32_t* sort_val;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
 
     // defaults for Gaussians that are not rendered
     int out_radius = 0;
-    uint32_t out_tiles = 0;
+    uint32_t out_tiles = 0, out_cells = 0;
     uint32_t out_key = 0xFFFFFFFFu;   // culled Gaussians sort to the back
     TileRect out_rect = {0, 0, 0, 0};
     bool visible = false;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         const unsigned rows = cy1 > cy0 ? cy1 - cy0 : 0u;
         out_tiles = rows * (rx1 - rx0);
         out_rect = {(uint16_t)rx0, (uint16_t)(rows ? cy0 : 0u), (uint16_t)rx1, (uint16_t)(rows ? cy1 : 0u)};
+        if (rows) out_cells = ((rx1 - 1) / CELL - rx0 / CELL + 1) * ((cy1 - 1) / CELL - cy0 / CELL + 1);
         out_key = __float_as_uint(p_view.z);
 
         // Screen-space half extents of the region where this Gaussian can reach alpha >= 1/255
@@ -211,13 +213,19 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
 
     p.radii[idx] = out_radius;
     p.tiles_touched[idx] = out_tiles;
+    p.cells_touched[idx] = out_cells;
     p.rect[idx] = out_rect;
     p.sort_key[idx] = out_key;
     p.sort_val[idx] = (uint32_t)idx;
 
-    // visible count (one atomic per warp)
-    const unsigned ballot = __ballot_sync(__activemask(), visible);
-    if (ballot != 0 && (threadIdx.x & 31) == (__ffs(ballot) - 1)) atomicAdd(&p.counters[1], __popc(ballot));
+    // visible count and total instance count R (one atomic each per warp)
+    const unsigned active = __activemask();
+    const unsigned ballot = __ballot_sync(active, visible);
+    const unsigned warp_tiles = __reduce_add_sync(active, out_tiles);
+    if (ballot != 0 && (threadIdx.x & 31) == (__ffs(ballot) - 1)) {
+        atomicAdd(&p.counters[1], __popc(ballot));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&p.counters[2]), (unsigned long long)warp_tiles);
+    }
 }
 
 int launch_preprocess_fwd(const GsrForwardArgs& a, const GeomState& g, int ty0, int ty1, cudaStream_t s) {
@@ -235,7 +243,7 @@ int launch_preprocess_fwd(const GsrForwardArgs& a, const GeomState& g, int ty0, 
     p.cov3D_precomp = a.cov3D_precomp; p.campos = a.campos;
     p.view = a.viewmatrix; p.proj = a.projmatrix;
     p.radii = a.radii; p.rec = g.rec; p.rgb = g.rgb; p.clamped = g.clamped; p.depths = g.depths;
-    p.tiles_touched = g.tiles_touched; p.rect = g.rect;
+    p.tiles_touched = g.tiles_touched; p.cells_touched = g.cells_touched; p.rect = g.rect;
     p.sort_key = g.key_a; p.sort_val = g.val_a; p.counters = g.counters;
     const int blocks = (a.P + 255) / 256;
     preprocess_fwd_kernel<<<blocks, 256, 0, s>>>(p);

@@ -174,6 +174,14 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
     }
 }
 
+int row_scan_u32(uint32_t* m, int rows, size_t cols, uint32_t* total, cudaStream_t s) {
+    if (rows <= 0 || cols == 0) return 0;
+    radix_rowscan_kernel<<<rows, 1024, 0, s>>>(m, (uint32_t)cols, total);
+    count_launches(1);
+    GSR_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int radix_num_passes(int begin_bit, int end_bit) {
     const int nbits = end_bit - begin_bit;
     return nbits <= 0 ? 0 : (nbits + RADIX_BITS - 1) / RADIX_BITS;

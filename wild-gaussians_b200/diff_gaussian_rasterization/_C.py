@@ -62,9 +62,9 @@ def _load():
     lib.gsr_abi_version.restype = c_int
     lib.gsr_last_error.restype = c_char_p
     lib.gsr_forward_sizes.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]
-    lib.gsr_forward_geometry.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, POINTER(c_int)]
-    lib.gsr_binning_sizes.argtypes = [c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]
-    lib.gsr_forward_render.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    lib.gsr_forward_geometry.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int)]
+    lib.gsr_binning_sizes.argtypes = [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]
+    lib.gsr_forward_render.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.gsr_forward_recolor.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsr_backward_scratch_bytes.argtypes = [c_int]
     lib.gsr_backward_scratch_bytes.restype = c_size_t
@@ -178,15 +178,15 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         geom = torch.empty((gb.value,), **byte)
         img = torch.empty((ib.value,), **byte)
         stream = _stream(dev)
-        R = c_int(0)
-        _check(_lib.gsr_forward_geometry(byref(a), geom.data_ptr(), img.data_ptr(), stream, byref(R)),
+        R, N1 = c_int(0), c_int(0)
+        _check(_lib.gsr_forward_geometry(byref(a), geom.data_ptr(), img.data_ptr(), stream, byref(R), byref(N1)),
                "gsr_forward_geometry")
         bb, sb = c_size_t(0), c_size_t(0)
-        _check(_lib.gsr_binning_sizes(P, W, H, R.value, byref(bb), byref(sb)), "gsr_binning_sizes")
+        _check(_lib.gsr_binning_sizes(P, W, H, R.value, N1.value, byref(bb), byref(sb)), "gsr_binning_sizes")
         binning = torch.empty((bb.value,), **byte)
         scratch = torch.empty((sb.value,), **byte)
         _check(_lib.gsr_forward_render(byref(a), geom.data_ptr(), img.data_ptr(), binning.data_ptr(),
-                                       scratch.data_ptr(), R.value, stream), "gsr_forward_render")
+                                       scratch.data_ptr(), R.value, N1.value, stream), "gsr_forward_render")
         # `scratch` goes back to torch's stream-ordered caching allocator here: any later
         # allocation on this stream is ordered after the kernels that use it.
         del scratch
