@@ -17,16 +17,12 @@ for p in (ROOT, os.path.join(ROOT, "wild-gaussians_b200"), os.path.join(ROOT, "t
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-
-
-@pytest.fixture(scope="session", autouse=True)
-def _built():
-    """Make sure the in-tree libraries exist (no-op when they are up to date)."""
+    # Make sure the in-tree libraries are up to date BEFORE any test module imports (and dlopens) them
+    # (no-op when they are newer than their sources).
     import __graft_entry__ as ge
     ge.build_lib()
     from oracle import cpu_oracle
     cpu_oracle.build()
-    yield
 
 
 def pytest_collection_modifyitems(config, items):

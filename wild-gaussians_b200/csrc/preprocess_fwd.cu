@@ -51,53 +51,57 @@ __device__ __forceinline__ float ndc_to_pix(float v, int S) {
     return ((v + 1.0) * S - 1.0) * 0.5;
 }
 
+// SH -> RGB (forward.cu:20-71).  The rounding sequence is part of the numerics contract (the clamp flags
+// and the colours must have the reference's bits), so every product / sum is spelled out with
+// non-contractable intrinsics in exactly the order nvcc emits for the reference (read off its SASS and
+// pinned by tests/golden): each term is accumulated with one fma, res = fma(w_k, sh_k, res).
 __device__ __forceinline__ V3 sh_to_rgb(int deg, const float* __restrict__ sh, float3 p, const float* __restrict__ campos,
                                         unsigned* clamp_bits) {
-    V3 pos = {p.x, p.y, p.z};
-    V3 cam = {campos[0], campos[1], campos[2]};
-    V3 dir = pos - cam;
-    const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-    dir.x = dir.x / len;
-    dir.y = dir.y / len;
-    dir.z = dir.z / len;
+    const float dx = __fsub_rn(p.x, campos[0]), dy = __fsub_rn(p.y, campos[1]), dz = __fsub_rn(p.z, campos[2]);
+    const float len = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
+    const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
 
-    V3 result = GSR_SH_C0 * ldv3(sh);
+    float res[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) res[c] = __fmul_rn(GSR_SH_C0, sh[c]);
+    auto acc = [&](float w, int k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) res[c] = __fmaf_rn(w, sh[3 * k + c], res[c]);
+    };
     if (deg > 0) {
-        const float x = dir.x, y = dir.y, z = dir.z;
-        result = result - GSR_SH_C1 * y * ldv3(sh + 3) + GSR_SH_C1 * z * ldv3(sh + 6) - GSR_SH_C1 * x * ldv3(sh + 9);
+        acc(-__fmul_rn(GSR_SH_C1, y), 1);
+        acc(__fmul_rn(GSR_SH_C1, z), 2);
+        acc(-__fmul_rn(GSR_SH_C1, x), 3);
         if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z;
-            const float xy = x * y, yz = y * z, xz = x * z;
-            result = result +
-                     GSR_SH_C2_0 * xy * ldv3(sh + 12) +
-                     GSR_SH_C2_1 * yz * ldv3(sh + 15) +
-                     GSR_SH_C2_2 * (2.0f * zz - xx - yy) * ldv3(sh + 18) +
-                     GSR_SH_C2_3 * xz * ldv3(sh + 21) +
-                     GSR_SH_C2_4 * (xx - yy) * ldv3(sh + 24);
+            const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+            const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+            acc(__fmul_rn(GSR_SH_C2_0, xy), 4);
+            acc(__fmul_rn(GSR_SH_C2_1, yz), 5);
+            acc(__fmul_rn(GSR_SH_C2_2, __fsub_rn(__fmaf_rn(2.0f, zz, -xx), yy)), 6);
+            acc(__fmul_rn(GSR_SH_C2_3, xz), 7);
+            acc(__fmul_rn(GSR_SH_C2_4, __fsub_rn(xx, yy)), 8);
             if (deg > 2) {
-                result = result +
-                         GSR_SH_C3_0 * y * (3.0f * xx - yy) * ldv3(sh + 27) +
-                         GSR_SH_C3_1 * xy * z * ldv3(sh + 30) +
-                         GSR_SH_C3_2 * y * (4.0f * zz - xx - yy) * ldv3(sh + 33) +
-                         GSR_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * ldv3(sh + 36) +
-                         GSR_SH_C3_4 * x * (4.0f * zz - xx - yy) * ldv3(sh + 39) +
-                         GSR_SH_C3_5 * z * (xx - yy) * ldv3(sh + 42) +
-                         GSR_SH_C3_6 * x * (xx - 3.0f * yy) * ldv3(sh + 45);
+                acc(__fmul_rn(__fmul_rn(GSR_SH_C3_0, y), __fmaf_rn(3.0f, xx, -yy)), 9);
+                acc(__fmul_rn(__fmul_rn(GSR_SH_C3_1, xy), z), 10);
+                acc(__fmul_rn(__fmul_rn(GSR_SH_C3_2, y), __fsub_rn(__fmaf_rn(4.0f, zz, -xx), yy)), 11);
+                acc(__fmul_rn(__fmul_rn(GSR_SH_C3_3, z), __fmaf_rn(-3.0f, yy, __fmaf_rn(-3.0f, xx, __fmul_rn(2.0f, zz)))), 12);
+                acc(__fmul_rn(__fmul_rn(GSR_SH_C3_4, x), __fsub_rn(__fmaf_rn(4.0f, zz, -xx), yy)), 13);
+                acc(__fmul_rn(__fmul_rn(GSR_SH_C3_5, z), __fsub_rn(xx, yy)), 14);
+                acc(__fmul_rn(__fmul_rn(GSR_SH_C3_6, x), __fmaf_rn(-3.0f, yy, xx)), 15);
             }
         }
     }
-    result.x += 0.5f;
-    result.y += 0.5f;
-    result.z += 0.5f;
     unsigned bits = 0;
-    if (result.x < 0) bits |= 1u;
-    if (result.y < 0) bits |= 2u;
-    if (result.z < 0) bits |= 4u;
+    V3 out;
+    float* o = &out.x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float r = __fadd_rn(res[c], 0.5f);
+        if (r < 0) bits |= 1u << c;
+        o[c] = fmaxf(r, 0.0f);
+    }
     *clamp_bits = bits;
-    result.x = fmaxf(result.x, 0.0f);
-    result.y = fmaxf(result.y, 0.0f);
-    result.z = fmaxf(result.z, 0.0f);
-    return result;
+    return out;
 }
 
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_constant__ PreFwdParams p) {
@@ -108,8 +112,12 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
     else if (threadIdx.x < 32) s_proj[threadIdx.x - 16] = p.proj[threadIdx.x - 16];
     __syncthreads();
 
+    __shared__ unsigned s_block_tiles, s_block_visible;
+    if (threadIdx.x == 0) { s_block_tiles = 0; s_block_visible = 0; }
+    __syncthreads();
+
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
+    const bool in_range = idx < p.P;
 
     // defaults for Gaussians that are not rendered
     int out_radius = 0;
@@ -118,13 +126,15 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
     TileRect out_rect = {0, 0, 0, 0};
     bool visible = false;
 
-    const float3 p_orig = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
+    float3 p_orig = {0.f, 0.f, 0.f};
+    if (in_range) p_orig = float3{p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
     const float4 p_hom = xform_point_4x4(p_orig, s_proj);
     const float p_w = 1.0f / (p_hom.w + 0.0000001f);
     const float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
     const float3 p_view = xform_point_4x3(p_orig, s_view);
 
     do {
+        if (!in_range) break;
         if (p_view.z <= NEAR_Z) {
             if (p.prefiltered) atomicExch(&p.counters[0], 1);
             break;
@@ -211,20 +221,26 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         p.depths[idx] = p_view.z;
     } while (false);
 
-    p.radii[idx] = out_radius;
-    p.tiles_touched[idx] = out_tiles;
-    p.cells_touched[idx] = out_cells;
-    p.rect[idx] = out_rect;
-    p.sort_key[idx] = out_key;
-    p.sort_val[idx] = (uint32_t)idx;
+    if (in_range) {
+        p.radii[idx] = out_radius;
+        p.tiles_touched[idx] = out_tiles;
+        p.cells_touched[idx] = out_cells;
+        p.rect[idx] = out_rect;
+        p.sort_key[idx] = out_key;
+        p.sort_val[idx] = (uint32_t)idx;
+    }
 
-    // visible count and total instance count R (one atomic each per warp)
-    const unsigned active = __activemask();
-    const unsigned ballot = __ballot_sync(active, visible);
-    const unsigned warp_tiles = __reduce_add_sync(active, out_tiles);
-    if (ballot != 0 && (threadIdx.x & 31) == (__ffs(ballot) - 1)) {
-        atomicAdd(&p.counters[1], __popc(ballot));
-        atomicAdd(reinterpret_cast<unsigned long long*>(&p.counters[2]), (unsigned long long)warp_tiles);
+    // visible count and total instance count R: warp reduce -> shared -> one global atomic per CTA
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, visible);
+    const unsigned warp_tiles = __reduce_add_sync(0xFFFFFFFFu, out_tiles);
+    if ((threadIdx.x & 31) == 0 && ballot != 0) {
+        atomicAdd(&s_block_visible, (unsigned)__popc(ballot));
+        atomicAdd(&s_block_tiles, warp_tiles);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_block_visible != 0) {
+        atomicAdd(&p.counters[1], (int)s_block_visible);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&p.counters[2]), (unsigned long long)s_block_tiles);
     }
 }
 

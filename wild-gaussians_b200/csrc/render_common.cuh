@@ -4,8 +4,7 @@
 
 namespace gsr {
 
-constexpr int RT_THREADS = 256;          // one thread per pixel of a 16x16 tile
-constexpr int RT_WARPS = RT_THREADS / 32;
+constexpr int RT_BATCH = 256;   // instances staged in shared memory per round
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -21,23 +20,33 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// Thread -> pixel mapping inside a tile: each warp owns a compact 8x4 pixel block (2 x 4 blocks per
-// tile) instead of the reference's 16x2 strip.  Per-pixel results do not depend on the mapping; the
-// compact block makes the per-warp culling below reject more Gaussians and keeps every 32-byte output
-// sector written by one warp.
-__device__ __forceinline__ void tile_pixel(int tid, int& lx, int& ly) {
-    const int warp = tid >> 5, lane = tid & 31;
-    lx = (warp & 1) * 8 + (lane & 7);
-    ly = (warp >> 1) * 4 + (lane >> 3);
-}
+// Thread -> pixel mapping inside a 16x16 tile.  A thread owns PPT pixels (1, 2 or 4) arranged PX x PY,
+// a warp owns a compact block of (8 PX) x (4 PY) pixels (the reference: one pixel per thread, a warp =
+// a 16x2 strip).  Per-pixel results do not depend on the mapping.  More pixels per thread amortise the
+// per-Gaussian shared-memory loads, loop control and (in the backward) the warp reduction over more
+// (pixel, Gaussian) pairs; the compact block keeps the per-warp culling selective and every 32-byte
+// output sector is written by one warp.
+template <int PPT>
+struct PixelMap {
+    static_assert(PPT == 1 || PPT == 2 || PPT == 4, "PPT must be 1, 2 or 4");
+    static constexpr int PX = PPT == 4 ? 2 : 1;
+    static constexpr int PY = PPT >= 2 ? 2 : 1;
+    static constexpr int THREADS = TILE * TILE / PPT;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int BW = 8 * PX, BH = 4 * PY;          // warp block in pixels
+    static constexpr int BLOCKS_X = TILE / BW;
+    __device__ static __forceinline__ void pixel(int tid, int k, int& lx, int& ly) {
+        const int warp = tid >> 5, lane = tid & 31;
+        lx = (warp % BLOCKS_X) * BW + (lane & 7) * PX + (k % PX);
+        ly = (warp / BLOCKS_X) * BH + (lane >> 3) * PY + (k / PX);
+    }
+};
 
-// Bounding box of the warp's (sub-pixel shifted) sample positions; lanes outside the image are ignored.
+// Bounding box of the warp's (sub-pixel shifted) sample positions; lanes/pixels outside the image are ignored.
 struct WarpBox {
     float x0, x1, y0, y1;
 };
-__device__ __forceinline__ WarpBox warp_box(float2 pixf, bool inside) {
-    float x0 = inside ? pixf.x : 3.0e38f, x1 = inside ? pixf.x : -3.0e38f;
-    float y0 = inside ? pixf.y : 3.0e38f, y1 = inside ? pixf.y : -3.0e38f;
+__device__ __forceinline__ WarpBox warp_box_reduce(float x0, float x1, float y0, float y1) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         x0 = fminf(x0, __shfl_xor_sync(0xFFFFFFFFu, x0, o));
