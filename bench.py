@@ -59,6 +59,18 @@ def peaks():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel, config):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
+    capture of this workload (profiles/ncu_traffic.json); None when no capture of that kernel/config is committed."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if t.get("config", "C3") != config:
+            return None
+        return t["dram_bytes_per_launch"].get(kernel)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed regions."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
@@ -70,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
         except Exception:
             self.proc = None
             return
@@ -343,7 +355,6 @@ def main():
     sampler.start()
     ms = time_steps(step, a.steps, a.warmup, dev, world)
     launches = (_C.launch_count() - launches0) // (a.steps + a.warmup) * a.steps
-    clocks = sampler.stop()
 
     # separate fwd / bwd times and per-stage times: K profiled steps right after the timed region
     R = state["R"]
@@ -377,6 +388,7 @@ def main():
         for k, v in _C.profile_read().items():
             acc.setdefault(k, []).append(v)
     _C.profile_enable(False)
+    clocks = sampler.stop()      # sampled over warm-up + timed steps + the profiled steps (same kernels, GPU busy throughout)
     stage_ms = {k: float(np.mean(v)) for k, v in acc.items()}
 
     value = P * N / (ms * 1e-3)
@@ -391,7 +403,7 @@ def main():
         dom = max(stages, key=lambda k: stages[k]["ms"])
         line["stages"] = stages
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                            "frac": stages[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                            "frac": stages[dom]["gbs"] / peak, "traffic": ncu_traffic(dom, a.config), "peak_source": peak_src,
                             "alg_bytes_per_launch": stages[dom]["alg_bytes"], "launch_ms": stages[dom]["ms"]}
         Bf, Bb = path_bytes(P, V, R, N, sh_M)
         line["roofline_path"] = {"bound": "hbm", "B_fwd": int(Bf), "B_bwd": int(Bb), "achieved": (Bf + Bb) / (ms * 1e-3) / 1e9,
