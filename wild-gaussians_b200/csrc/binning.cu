@@ -198,18 +198,23 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __rest
 }
 
 // ---- level 2c: scatter ------------------------------------------------------------------------------
+// One warp per unit.  Lane l owns the running output position of local tiles l and l + 32 (column l & 7, rows
+// l >> 3 and 4 + (l >> 3) of the cell).  The unit's coarse items are walked IN ORDER, 32 at a time: every lane
+// first turns its own item into an 8-bit column mask and an 8-bit row mask (staged in shared memory with the
+// Gaussian id), then the warp loops over the staged items and each lane appends the id to the lists of the tiles
+// it owns -- no ballots, no ranks: the order inside a tile list is the walk order = depth order.
 __global__ void __launch_bounds__(256) cell_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                            const uint32_t* __restrict__ unit_base,
                                                            const uint2* __restrict__ cell_range, uint32_t num_cells,
                                                            const uint32_t* __restrict__ Pm, const uint32_t* __restrict__ row_total,
                                                            uint32_t cap, const uint32_t* __restrict__ tile_start, int cells_x,
                                                            int grid_x, int grid_y, uint32_t* __restrict__ point_list) {
+    __shared__ uint2 s_item[8][32];   // {column mask | row mask << 8, Gaussian id}
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t u = blockIdx.x * 8 + warp;
     const uint32_t num_units = unit_base[num_cells];
     if (u >= num_units) return;
     const UnitInfo ui = unit_info(unit_base, cell_range, num_cells, u);
-    // running output position of local tiles `lane` (pos[0]) and `lane + 32` (pos[1])
     uint32_t pos[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -221,30 +226,24 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const uint32_t* __res
                 prefix_at(Pm, row_total, cap, t, ui.first_unit_of_cell);
         pos[h] = p;
     }
-    const unsigned lt = (1u << lane) - 1u;
+    const int sx = lane & 7, sy0 = 8 + (lane >> 3), sy1 = 12 + (lane >> 3);
     for (uint32_t base = 0; base < ui.count; base += 32) {
-        const bool valid = base + lane < ui.count;
-        uint32_t key = 0, id = 0;
-        if (valid) {
-            key = keys[ui.first + base + lane];
-            id = vals[ui.first + base + lane];
+        const int nitems = (int)min(32u, ui.count - base);
+        __syncwarp();
+        if (lane < nitems) {
+            const uint32_t key = keys[ui.first + base + lane];
+            const uint32_t x0 = (key >> 16) & 15u, y0 = (key >> 20) & 15u, x1 = (key >> 24) & 15u, y1 = (key >> 28) & 15u;
+            const uint32_t cm = ((1u << x1) - 1u) & ~((1u << x0) - 1u);
+            const uint32_t rm = ((1u << y1) - 1u) & ~((1u << y0) - 1u);
+            s_item[warp][lane] = make_uint2(cm | (rm << 8), vals[ui.first + base + lane]);
         }
-        const int x0 = (key >> 16) & 15, y0 = (key >> 20) & 15;
-        const int x1 = valid ? (key >> 24) & 15 : 0, y1 = valid ? (key >> 28) & 15 : 0;
-        // rows of the cell touched by any of the 32 items
-        const int ymin = __reduce_min_sync(0xFFFFFFFFu, valid ? y0 : CELL);
-        const int ymax = __reduce_max_sync(0xFFFFFFFFu, y1);
-        for (int y = ymin; y < ymax; ++y) {
-            const bool in_row = y >= y0 && y < y1;
-#pragma unroll
-            for (int x = 0; x < CELL; ++x) {
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, in_row && x >= x0 && x < x1);
-                if (m == 0) continue;
-                const int t = y * CELL + x;
-                const uint32_t b = __shfl_sync(0xFFFFFFFFu, (t & 32) ? pos[1] : pos[0], t & 31);
-                if (m & (1u << lane)) point_list[b + __popc(m & lt)] = id;
-                if (lane == (t & 31)) pos[t >> 5] += __popc(m);
-            }
+        __syncwarp();
+#pragma unroll 4
+        for (int i = 0; i < nitems; ++i) {
+            const uint2 it = s_item[warp][i];
+            const uint32_t c = it.x >> sx;
+            if (c & (it.x >> sy0) & 1u) point_list[pos[0]++] = it.y;
+            if (c & (it.x >> sy1) & 1u) point_list[pos[1]++] = it.y;
         }
     }
 }

@@ -85,6 +85,20 @@ __device__ __forceinline__ int butterfly10(float (&v)[10], int lane) {
     return idx < 0 ? 15 : idx + 5 * b4;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// What one lane accumulates per Gaussian (summed over its pixels, then over the warp, then over the tile).
+// With w = G * dL/dalpha of a blended (pixel, Gaussian) pair and d = mean2D - pixel:
+//   0: sum w*dx   1: sum w*dy   2: sum |dL/dmean2D.x| + |dL/dmean2D.y|   3: sum w*dx*dx   4: sum w*dx*dy
+//   5: sum w*dy*dy   6: sum w (= dL/d(opacity*coef))   7..9: sum alpha*T*dL/dpixel[ch] (= dL/dcolour)
+// The reference's per-pair gradient terms (backward.cu:574-603) are linear in these moments:
+//   dL/dmean2D.x = -o W/2 (A s0 + B s1)   dL/dmean2D.y = -o H/2 (C s1 + B s0)   dL/dconic = -o/2 (s3, s4, s5)
+// (o = opacity*coef, (A, B, C) = conic), so the linear map is applied once per (tile, Gaussian) when the tile
+// flushes its sums instead of once per pixel pair.
 template <int PPT>
 __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(const __grid_constant__ RenderBwdParams p) {
     using PM = PixelMap<PPT>;
@@ -93,18 +107,22 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(cons
     __shared__ uint32_t s_id[RT_BATCH];
     __shared__ __align__(16) float4 s_geo[RT_BATCH];   // {x, y, hx, hy}
     __shared__ __align__(16) float4 s_con[RT_BATCH];   // {conic.x, conic.y, conic.z, opacity}
-    __shared__ float s_col[RT_BATCH][3];
+    __shared__ __align__(16) float4 s_col[RT_BATCH];   // {r, g, b, -}
     __shared__ __align__(16) float s_acc[RT_BATCH][RB_ACC];
     __shared__ uint32_t s_max[WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + p.ty0;
     const size_t plane = (size_t)p.H * p.W;
+    const float bg0 = p.bg[0], bg1 = p.bg[1], bg2 = p.bg[2];
 
+    // per-pixel state.  Tb = -T_final * (bg . dL/dpixel): the background term of dL/dalpha is Tb / (1 - alpha)
+    // (backward.cu:576-579).  rdot / last_cd / last_alpha carry the reference's accum_rec / last_color / last_alpha
+    // recurrence (backward.cu:560-572) projected on dL/dpixel: only (colour - accum_rec) . dL/dpixel is ever used.
     float2 pixf[PPT];
-    float T_final[PPT], T[PPT], last_alpha[PPT];
+    float T[PPT], Tb[PPT], rdot[PPT], last_cd[PPT], last_alpha[PPT];
     uint32_t last_contributor[PPT];
-    float accum_rec[PPT][3], last_color[PPT][3], dL_dpixel[PPT][3];
+    float dL_dpixel[PPT][3];
     float bx0 = 3.0e38f, bx1 = -3.0e38f, by0 = 3.0e38f, by1 = -3.0e38f;
     uint32_t thread_last = 0;
 #pragma unroll
@@ -115,23 +133,23 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(cons
         const unsigned pix_id = p.W * py + px;
         const bool inside = px < (unsigned)p.W && py < (unsigned)p.H;
         pixf[k] = {(float)px, (float)py};
-        T_final[k] = 0.f;
+        T[k] = 0.f;
         last_contributor[k] = 0;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) { accum_rec[k][ch] = 0.f; last_color[k][ch] = 0.f; dL_dpixel[k][ch] = 0.f; }
-        last_alpha[k] = 0.f;
+        for (int ch = 0; ch < 3; ++ch) dL_dpixel[k][ch] = 0.f;
         if (inside) {
             const float2 so = p.subpixel_offset[pix_id];
             pixf[k].x += so.x;
             pixf[k].y += so.y;
-            T_final[k] = p.final_T[pix_id];
+            T[k] = p.final_T[pix_id];
             last_contributor[k] = p.n_contrib[pix_id];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) dL_dpixel[k][ch] = p.dL_dpix[ch * plane + pix_id];
             bx0 = fminf(bx0, pixf[k].x); bx1 = fmaxf(bx1, pixf[k].x);
             by0 = fminf(by0, pixf[k].y); by1 = fmaxf(by1, pixf[k].y);
         }
-        T[k] = T_final[k];
+        Tb[k] = -T[k] * (bg0 * dL_dpixel[k][0] + bg1 * dL_dpixel[k][1] + bg2 * dL_dpixel[k][2]);
+        rdot[k] = 0.f; last_cd[k] = 0.f; last_alpha[k] = 0.f;
         thread_last = max(thread_last, last_contributor[k]);
     }
     const WarpBox box = warp_box_reduce(bx0, bx1, by0, by1);
@@ -147,10 +165,19 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(cons
     const int total = (int)min(tile_last, range.y - range.x);   // instances [range.x, range.x+total) matter
     const int rounds = (total + RT_BATCH - 1) / RT_BATCH;
 
-    const float bg0 = p.bg[0], bg1 = p.bg[1], bg2 = p.bg[2];
     // Gradient of pixel coordinate w.r.t. normalized screen-space viewport coordinates (-1 to 1)
-    const float ddelx_dx = 0.5 * p.W;
-    const float ddely_dy = 0.5 * p.H;
+    const float ddelx_dx = 0.5f * p.W;
+    const float ddely_dy = 0.5f * p.H;
+
+    // which butterfly slot this lane ends up holding is a function of the lane only
+    int my_slot;
+    {
+        float dummy[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) dummy[q] = 0.f;
+        my_slot = butterfly10(dummy, lane);
+    }
+    const bool slot_owner = (lane & 1) == 0 && my_slot < 10;
 
     int toDo = total;
     for (int r = 0; r < rounds; ++r, toDo -= RT_BATCH) {
@@ -165,12 +192,11 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(cons
                 const float4* src = p.rec + 2 * (size_t)id;
                 s_geo[slot] = src[0];
                 s_con[slot] = src[1];
-                s_col[slot][0] = p.colors[3 * (size_t)id + 0];
-                s_col[slot][1] = p.colors[3 * (size_t)id + 1];
-                s_col[slot][2] = p.colors[3 * (size_t)id + 2];
+                const float* c = p.colors + 3 * (size_t)id;
+                s_col[slot] = make_float4(c[0], c[1], c[2], 0.f);
             }
-#pragma unroll
-            for (int k = 0; k < RB_ACC; ++k) s_acc[slot][k] = 0.f;
+            float4* a = reinterpret_cast<float4*>(s_acc[slot]);
+            a[0] = a[1] = a[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
 
@@ -178,88 +204,83 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(cons
         // 0-based list position of staged entry j: pos(j) = first_pos - j  (walking back to front)
         const int first_pos = total - 1 - r * RT_BATCH;
 
-        // per-warp culling: staged Gaussians that are in front of this warp's deepest contributor and whose
-        // alpha >= 1/255 footprint can touch the warp's pixel block
-        unsigned mask[RT_BATCH / 32];
-#pragma unroll
+#pragma unroll 1
         for (int w = 0; w < RT_BATCH / 32; ++w) {
-            const int j = w * 32 + lane;
-            const bool rel = j < n && (uint32_t)(first_pos - j) < warp_last && box_may_touch(s_geo[j], box);
-            mask[w] = __ballot_sync(0xFFFFFFFFu, rel);
-        }
-#pragma unroll
-        for (int w = 0; w < RT_BATCH / 32; ++w) {
-            unsigned mm = mask[w];
+            // per-warp culling: staged Gaussians that are in front of this warp's deepest contributor and whose
+            // alpha >= 1/255 footprint can touch the warp's pixel block
+            const int jl = w * 32 + lane;
+            const bool rel = jl < n && (uint32_t)(first_pos - jl) < warp_last && box_may_touch(s_geo[jl], box);
+            unsigned mm = __ballot_sync(0xFFFFFFFFu, rel);
             while (mm) {
                 const int j = w * 32 + __ffs(mm) - 1;
                 mm &= mm - 1;
                 const uint32_t pos = (uint32_t)(first_pos - j);
                 const float4 geo = s_geo[j];
                 const float4 con_o = s_con[j];
-                const float c0 = s_col[j][0], c1 = s_col[j][1], c2 = s_col[j][2];
 
-                float v[10];
-#pragma unroll
-                for (int q = 0; q < 10; ++q) v[q] = 0.f;
+                // pass 1: which of this lane's pixels blend this Gaussian (same tests, same expressions as the
+                // forward: backward.cu:529-546 / forward.cu:353-368)
+                float G[PPT], alpha[PPT];
+                float2 d[PPT];
                 bool any_active = false;
 #pragma unroll
                 for (int k = 0; k < PPT; ++k) {
+                    d[k] = {geo.x - pixf[k].x, geo.y - pixf[k].y};
+                    const float power = -0.5f * (con_o.x * d[k].x * d[k].x + con_o.z * d[k].y * d[k].y) - con_o.y * d[k].x * d[k].y;
+                    const float g = expf(power);
+                    const float a = min(0.99f, con_o.w * g);
                     // the reference visits an instance iff its position is below the pixel's n_contrib
                     // (backward.cu:529-533); pixels outside the image have n_contrib = 0
-                    if (!(pos < last_contributor[k])) continue;
-                    const float2 d = {geo.x - pixf[k].x, geo.y - pixf[k].y};
-                    const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-                    if (power > 0.0f) continue;
-                    const float G = expf(power);
-                    const float alpha = min(0.99f, con_o.w * G);
-                    if (alpha < 1.0f / 255.0f) continue;
-                    any_active = true;
-
-                    // one reciprocal serves T / (1 - alpha) and T_final / (1 - alpha) (backward.cu:548,579);
-                    // gradients are compared at 1e-3, the reciprocal is good to 1 ulp
-                    const float inv = __frcp_rn(1.f - alpha);
-                    T[k] = T[k] * inv;
-                    const float dchannel_dcolor = alpha * T[k];
-                    float dL_dalpha = 0.0f;
-                    const float cc[3] = {c0, c1, c2};
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        accum_rec[k][ch] = last_alpha[k] * last_color[k][ch] + (1.f - last_alpha[k]) * accum_rec[k][ch];
-                        last_color[k][ch] = cc[ch];
-                        const float dL_dchannel = dL_dpixel[k][ch];
-                        dL_dalpha += (cc[ch] - accum_rec[k][ch]) * dL_dchannel;
-                        v[7 + ch] += dchannel_dcolor * dL_dchannel;
-                    }
-                    dL_dalpha *= T[k];
-                    last_alpha[k] = alpha;
-
-                    const float bg_dot_dpixel = bg0 * dL_dpixel[k][0] + bg1 * dL_dpixel[k][1] + bg2 * dL_dpixel[k][2];
-                    dL_dalpha += (-T_final[k] * inv) * bg_dot_dpixel;
-
-                    const float dL_dG = con_o.w * dL_dalpha;
-                    const float gdx = G * d.x;
-                    const float gdy = G * d.y;
-                    const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-                    const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-
-                    const float gx = dL_dG * dG_ddelx * ddelx_dx;
-                    const float gy = dL_dG * dG_ddely * ddely_dy;
-                    v[0] += gx;
-                    v[1] += gy;
-                    v[2] += fabsf(gx) + fabsf(gy);
-                    v[3] += -0.5f * gdx * d.x * dL_dG;
-                    v[4] += -0.5f * gdx * d.y * dL_dG;
-                    v[5] += -0.5f * gdy * d.y * dL_dG;
-                    v[6] += G * dL_dalpha;
+                    const bool act = pos < last_contributor[k] && !(power > 0.0f) && !(a < 1.0f / 255.0f);
+                    // a pair that does not blend is carried through the arithmetic below as G = alpha = 0: T, the
+                    // sums and the recurrence are then unchanged (the pending accum_rec update is merely applied
+                    // one step early, which commutes)
+                    G[k] = act ? g : 0.f;
+                    alpha[k] = act ? a : 0.f;
+                    any_active |= act;
                 }
                 if (!__any_sync(0xFFFFFFFFu, any_active)) continue;   // warp-uniform
 
-                const int slot = butterfly10(v, lane);
-                if ((lane & 1) == 0 && slot < 10) atomicAdd(&s_acc[j][slot], v[0]);
+                const float4 col = s_col[j];
+                const float kx = fabsf(con_o.w) * ddelx_dx, ky = fabsf(con_o.w) * ddely_dy;
+                float v[10];
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) {
+                    // T before this splat; 1 - alpha is in [0.01, 1], the approximate reciprocal is good to 1 ulp
+                    // and gradients are compared at 1e-3 (backward.cu:548,579 divide twice)
+                    const float inv = rcp_approx(1.f - alpha[k]);
+                    T[k] *= inv;
+                    const float aT = alpha[k] * T[k];
+                    rdot[k] = fmaf(last_alpha[k], last_cd[k] - rdot[k], rdot[k]);
+                    const float cd = col.x * dL_dpixel[k][0] + col.y * dL_dpixel[k][1] + col.z * dL_dpixel[k][2];
+                    last_cd[k] = cd;
+                    last_alpha[k] = alpha[k];
+                    const float dL_dalpha = fmaf(cd - rdot[k], T[k], Tb[k] * inv);
+                    const float wgt = G[k] * dL_dalpha;
+                    const float wx = wgt * d[k].x, wy = wgt * d[k].y;
+                    const float t1 = con_o.x * wx + con_o.y * wy;
+                    const float t2 = con_o.z * wy + con_o.y * wx;
+                    const float ab = fmaf(fabsf(t2), ky, fabsf(t1) * kx);
+                    if (k == 0) {
+                        v[0] = wx; v[1] = wy; v[2] = ab;
+                        v[3] = wx * d[k].x; v[4] = wx * d[k].y; v[5] = wy * d[k].y;
+                        v[6] = wgt;
+                        v[7] = aT * dL_dpixel[k][0]; v[8] = aT * dL_dpixel[k][1]; v[9] = aT * dL_dpixel[k][2];
+                    } else {
+                        v[0] += wx; v[1] += wy; v[2] += ab;
+                        v[3] = fmaf(wx, d[k].x, v[3]); v[4] = fmaf(wx, d[k].y, v[4]); v[5] = fmaf(wy, d[k].y, v[5]);
+                        v[6] += wgt;
+                        v[7] = fmaf(aT, dL_dpixel[k][0], v[7]); v[8] = fmaf(aT, dL_dpixel[k][1], v[8]);
+                        v[9] = fmaf(aT, dL_dpixel[k][2], v[9]);
+                    }
+                }
+                butterfly10(v, lane);
+                if (slot_owner) atomicAdd(&s_acc[j][my_slot], v[0]);
             }
         }
         __syncthreads();
-        // one flush per visited Gaussian per tile: three 128-bit reductions (skipped when nothing landed)
+        // one flush per visited Gaussian per tile: moments -> gradient terms, three 128-bit reductions
+        // (skipped when nothing landed)
 #pragma unroll
         for (int q = 0; q < PPT; ++q) {
             const int slot = q * THREADS + tid;
@@ -271,9 +292,14 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(cons
                 const bool any = (a0.x != 0.f) | (a0.y != 0.f) | (a0.z != 0.f) | (a0.w != 0.f) | (a1.x != 0.f) |
                                  (a1.y != 0.f) | (a1.z != 0.f) | (a1.w != 0.f) | (a2.x != 0.f) | (a2.y != 0.f);
                 if (any) {
+                    const float4 con_o = s_con[slot];
+                    const float o = con_o.w;
+                    const float gx = -o * ddelx_dx * (con_o.x * a0.x + con_o.y * a0.y);
+                    const float gy = -o * ddely_dy * (con_o.z * a0.y + con_o.y * a0.x);
+                    const float h = -0.5f * o;
                     float* dst = p.accum + (size_t)s_id[slot] * RB_ACC;
-                    red_add_v4(dst + 0, a0.x, a0.y, a0.z, a0.w);
-                    red_add_v4(dst + 4, a1.x, a1.y, a1.z, a1.w);
+                    red_add_v4(dst + 0, gx, gy, a0.z, h * a0.w);
+                    red_add_v4(dst + 4, h * a1.x, h * a1.y, a1.z, a1.w);
                     red_add_v4(dst + 8, a2.x, a2.y, 0.f, 0.f);
                 }
             }

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_fwd_kernel(cons
     constexpr int THREADS = PM::THREADS;
     __shared__ __align__(16) float4 s_geo[2][RT_BATCH];   // {x, y, hx, hy}
     __shared__ __align__(16) float4 s_con[2][RT_BATCH];   // {conic.x, conic.y, conic.z, opacity}
-    __shared__ float s_col[2][RT_BATCH][3];
+    __shared__ __align__(16) float4 s_col[2][RT_BATCH];   // {r, g, b, -}
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile_x = blockIdx.x, tile_y = blockIdx.y + p.ty0;
@@ -86,9 +86,10 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_fwd_kernel(cons
                 cp_async_16(&s_geo[buf][slot], src);
                 cp_async_16(&s_con[buf][slot], src + 1);
                 const float* c = p.colors + 3 * (size_t)ids[q];
-                cp_async_4(&s_col[buf][slot][0], c);
-                cp_async_4(&s_col[buf][slot][1], c + 1);
-                cp_async_4(&s_col[buf][slot][2], c + 2);
+                float* cdst = reinterpret_cast<float*>(&s_col[buf][slot]);
+                cp_async_4(cdst, c);
+                cp_async_4(cdst + 1, c + 1);
+                cp_async_4(cdst + 2, c + 2);
             }
         }
     };
@@ -130,20 +131,15 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_fwd_kernel(cons
             const int n = min(RT_BATCH, toDo);
             const uint32_t round_base = (uint32_t)(r * RT_BATCH);
             if (__any_sync(0xFFFFFFFFu, live != 0)) {
-                // which of the staged Gaussians can touch this warp's pixels?
-                unsigned mask[RT_BATCH / 32];
-#pragma unroll
+                // which of the staged Gaussians can touch this warp's pixels?  32 at a time: one ballot, then only
+                // the set bits are blended
+#pragma unroll 1
                 for (int w = 0; w < RT_BATCH / 32; ++w) {
-                    const int j = w * 32 + lane;
-                    mask[w] = __ballot_sync(0xFFFFFFFFu, j < n && box_may_touch(s_geo[buf][j], box));
-                }
-#pragma unroll
-                for (int w = 0; w < RT_BATCH / 32; ++w) {
-                    unsigned mm = mask[w];
+                    const int jl = w * 32 + lane;
+                    unsigned mm = __ballot_sync(0xFFFFFFFFu, jl < n && box_may_touch(s_geo[buf][jl], box));
                     while (mm) {
                         const int j = w * 32 + __ffs(mm) - 1;
                         mm &= mm - 1;
-                        if (live == 0) continue;
                         const float4 geo = s_geo[buf][j];
                         const float4 con_o = s_con[buf][j];
 #pragma unroll
@@ -161,9 +157,10 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_fwd_kernel(cons
                                 live &= ~(1u << k);
                                 continue;
                             }
-                            C0[k] += s_col[buf][j][0] * alpha * T[k];
-                            C1[k] += s_col[buf][j][1] * alpha * T[k];
-                            C2[k] += s_col[buf][j][2] * alpha * T[k];
+                            const float4 col = s_col[buf][j];
+                            C0[k] += col.x * alpha * T[k];
+                            C1[k] += col.y * alpha * T[k];
+                            C2[k] += col.z * alpha * T[k];
                             T[k] = test_T;
                             // 1-based position of this instance in the tile's list (forward.cu:349,382)
                             last_contributor[k] = round_base + (uint32_t)j + 1u;
