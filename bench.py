@@ -334,7 +334,7 @@ def main():
         state = {}
         def step():
             R, color, radii, geom, binning, img = _C.rasterize_gaussians(*call_args(d))
-            grads = _C.rasterize_gaussians_backward(*backward_args(d, radii, geom, R, binning, img))
+            grads = _C.rasterize_gaussians_backward_lean(*backward_args(d, radii, geom, R, binning, img))
             state.update(R=R, radii=radii, geom=geom, binning=binning, img=img)
     else:
         state = {}
@@ -379,7 +379,7 @@ def main():
             e0.record()
             Rr, color, radii, geom, binning, img = _C.rasterize_gaussians(*call_args(d))
             e1.record()
-            _C.rasterize_gaussians_backward(*backward_args(d, radii, geom, Rr, binning, img))
+            _C.rasterize_gaussians_backward_lean(*backward_args(d, radii, geom, Rr, binning, img))
             e2.record()
         else:
             e0.record(); step(); e1.record(); e2.record()

@@ -12,6 +12,7 @@
 // (backward.cu:199-217) are kept as they are.
 #include "common.cuh"
 #include "gaussian_math.cuh"
+#include <cstdlib>
 
 namespace gsr {
 
@@ -143,7 +144,8 @@ __device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const flo
     return dnormvdv3(float3{dir_orig.x, dir_orig.y, dir_orig.z}, dL_ddir);
 }
 
-__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const __grid_constant__ PreBwdParams p) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __grid_constant__ PreBwdParams p) {
     __shared__ float s_view[16];
     __shared__ float s_proj[16];
     if (threadIdx.x < 16) s_view[threadIdx.x] = p.view[threadIdx.x];
@@ -396,7 +398,14 @@ int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, const Bw
     p.dL_dmean2D = a.dL_dmean2D; p.dL_dconic = a.dL_dconic; p.dL_dopacity = a.dL_dopacity;
     p.dL_dcolor = a.dL_dcolor; p.dL_dmean3D = a.dL_dmean3D; p.dL_dcov3D = a.dL_dcov3D;
     p.dL_dsh = a.dL_dsh; p.dL_dscale = a.dL_dscale; p.dL_drot = a.dL_drot;
-    preprocess_bwd_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(p);
+    static int occ = -1;
+    if (occ < 0) {
+        const char* e = getenv("GSR_PREBWD_OCC");    // tuning aid: resident CTAs per SM the register allocation targets
+        occ = e ? atoi(e) : 3;
+    }
+    if (occ >= 4) preprocess_bwd_kernel<4><<<(a.P + 255) / 256, 256, 0, s>>>(p);
+    else if (occ == 3) preprocess_bwd_kernel<3><<<(a.P + 255) / 256, 256, 0, s>>>(p);
+    else preprocess_bwd_kernel<2><<<(a.P + 255) / 256, 256, 0, s>>>(p);
     count_launches(1);
     return 0;
 }

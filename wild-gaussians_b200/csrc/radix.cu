@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
                                                                    const uint32_t* __restrict__ total, uint32_t ctas) {
     __shared__ uint32_t s_cnt[RS_WARPS][RADIX];   // per-warp digit counters, later global bases
     __shared__ uint32_t s_digit_base[RADIX];
+    __shared__ uint32_t s_key[RS_CHUNK];
+    __shared__ uint32_t s_val[RS_CHUNK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
 
@@ -163,28 +165,53 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
         rank[r] = (uint16_t)(old + __popc(peers & lt_mask));
     }
     __syncthreads();
-    // per digit: running offset over warps + global base of this CTA -> s_cnt becomes the
-    // absolute output position of the first item of (warp, digit)
+    // Local (CTA-wide) stable order: per digit, running offset over the warps, then an exclusive scan over
+    // the digits; s_cnt[w][d] becomes the position of the first item of (warp, digit) in the CTA's sorted
+    // chunk and s_digit_base[d] the difference between that chunk position and the global output position.
     {
+        __shared__ uint32_t s_w2[RS_WARPS];
         const int d = threadIdx.x;
-        uint32_t run = s_digit_base[d];
+        uint32_t run = 0;
+        uint32_t c[RS_WARPS];
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            const uint32_t c = s_cnt[w][d];
-            s_cnt[w][d] = run;
-            run += c;
+        for (int w = 0; w < RS_WARPS; ++w) { c[w] = s_cnt[w][d]; run += c[w]; }
+        uint32_t x = run;     // inclusive scan of the digit totals of this CTA
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
         }
+        if (lane == 31) s_w2[warp] = x;
+        __syncthreads();
+        uint32_t off = 0;
+        for (int w = 0; w < warp; ++w) off += s_w2[w];
+        uint32_t loc = off + x - run;   // first chunk position of digit d
+        s_digit_base[d] -= loc;         // global position = chunk position + s_digit_base[d]  (mod 2^32)
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) { s_cnt[w][d] = loc; loc += c[w]; }
     }
     __syncthreads();
+    // stage the chunk in sorted order, then write it out: consecutive threads write consecutive addresses
+    // inside every digit run (the unstaged version issued one scattered 4-byte store per item and array)
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const size_t i = base + r * 32 + lane;
         if (i < n) {
             const uint32_t d = (key[r] >> shift) & mask;
-            const uint32_t pos = s_cnt[warp][d] + rank[r];
-            if (WRITE_KEYS) keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            const uint32_t li = s_cnt[warp][d] + rank[r];
+            s_key[li] = key[r];
+            s_val[li] = val[r];
         }
+    }
+    __syncthreads();
+    const size_t cta_base = (size_t)blockIdx.x * RS_CHUNK;
+    const uint32_t cta_n = (uint32_t)min((size_t)RS_CHUNK, n - cta_base);
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < cta_n; i += RS_THREADS) {
+        const uint32_t k = s_key[i];
+        const uint32_t pos = i + s_digit_base[(k >> shift) & mask];
+        if (WRITE_KEYS) keys_out[pos] = k;
+        vals_out[pos] = s_val[i];
     }
 }
 

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(cons
 }
 
 #ifndef GSR_BWD_PPT
-#define GSR_BWD_PPT 1     // default pixels per thread; GSR_BWD_PPT in the environment overrides (tuning aid)
+#define GSR_BWD_PPT 2     // default pixels per thread; GSR_BWD_PPT in the environment overrides (tuning aid)
 #endif
 
 static int bwd_ppt() {

@@ -195,8 +195,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 
 def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rotations, scale_modifier,
                    cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
-                   dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug):
-    """mode: "both" (gsr_backward), "partials" (returns the [P,12] accumulator), "finalize" (consumes it)."""
+                   dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug,
+                   want_cov3D=True):
+    """mode: "both" (gsr_backward), "partials" (returns the [P,12] accumulator), "finalize" (consumes it).
+    want_cov3D=False (autograd path with scales/rotations): dL_dcov3D is an intermediate nobody reads, so it
+    is neither allocated nor written (24 B per Gaussian) and None is returned in its place."""
     dev = means3D.device
     P = int(means3D.size(0))
     H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
@@ -212,7 +215,8 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
             dL_dmeans2D = alloc((P, 3), **f32)
             dL_dcolors = alloc((P, NUM_CHANNELS), **f32)
             dL_dopacity = alloc((P, 1), **f32)
-            dL_dcov3D = alloc((P, 6), **f32)
+            skip_cov3D = have_scales and not want_cov3D
+            dL_dcov3D = None if skip_cov3D else alloc((P, 6), **f32)
             dL_dsh = alloc((P, M, 3), **f32)
             dL_dscales = alloc((P, 3), **f32) if have_scales else torch.zeros((P, 3), **f32)
             dL_drotations = alloc((P, 4), **f32) if have_scales else torch.zeros((P, 4), **f32)
@@ -245,7 +249,8 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
         if outs is not None:
             a.dL_dmean2D = dL_dmeans2D.data_ptr(); a.dL_dconic = None
             a.dL_dopacity = dL_dopacity.data_ptr(); a.dL_dcolor = dL_dcolors.data_ptr()
-            a.dL_dmean3D = dL_dmeans3D.data_ptr(); a.dL_dcov3D = dL_dcov3D.data_ptr()
+            a.dL_dmean3D = dL_dmeans3D.data_ptr()
+            a.dL_dcov3D = None if dL_dcov3D is None else dL_dcov3D.data_ptr()
             a.dL_dsh = _ptr(dL_dsh)
             a.dL_dscale = dL_dscales.data_ptr() if have_scales else None
             a.dL_drot = dL_drotations.data_ptr() if have_scales else None
@@ -268,6 +273,12 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                           dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug)
 
 
+def rasterize_gaussians_backward_lean(*args):
+    """Same as ``rasterize_gaussians_backward`` but without materialising ``dL_dcov3D`` when scales/rotations
+    are given (its slot in the returned tuple is None).  Used by the autograd function of this package."""
+    return _backward_impl("both", None, *args, want_cov3D=False)
+
+
 def rasterize_gaussians_backward_partials(*args):
     """First half of the backward for the tile-row sharded path: this shard's per-Gaussian partial sums as a
     flat fp32 tensor whose first ``P*12`` entries are the ``[P,12]`` accumulator (same 23 arguments)."""
@@ -276,7 +287,7 @@ def rasterize_gaussians_backward_partials(*args):
 
 def rasterize_gaussians_backward_finalize(accum, *args):
     """Second half: per-Gaussian chain rule from the (all-reduced) accumulator to the 8 gradient tensors."""
-    return _backward_impl("finalize", accum, *args)
+    return _backward_impl("finalize", accum, *args, want_cov3D=False)
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):
