@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const uint32_t* __res
 // entries) ncu shows 37.5 M single-sector L2 write requests, 227 MB DRAM written + 159 MB read back for partial
 // sectors, 0.36 ms.  Staging turns them into ~3 M requests.
 // A unit whose output does not fit the staging buffer (very large splats) takes the direct path.
-constexpr int SQ_ENTRIES = 2560;           // staging capacity per warp (a unit of 256 items averages ~1700 at C3)
+constexpr int SQ_ENTRIES = 2048;           // staging capacity per warp (a unit of 256 items averages ~1800 at C3)
 constexpr int SQ_WARPS = 8;
 constexpr int SQ_WARP_WORDS = SQ_ENTRIES + 32 * 4;           // staging + 32 item records (uint4)
 constexpr size_t SQ_SMEM = (size_t)SQ_WARPS * SQ_WARP_WORDS * sizeof(uint32_t);
@@ -269,6 +269,67 @@ constexpr size_t SQ_SMEM = (size_t)SQ_WARPS * SQ_WARP_WORDS * sizeof(uint32_t);
 __device__ __forceinline__ void sts_append(uint32_t& addr, uint32_t v, uint32_t hit) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t@p add.u32 %0, %0, 4;\n\t}"
                  : "+r"(addr) : "r"(v), "r"(hit) : "memory");
+}
+
+// 16-byte record of one coarse item: coverage bits of local tiles 0-31 and 32-63 (bit 8 y + x), Gaussian id
+__device__ __forceinline__ uint4 item_record(uint32_t key, uint32_t id) {
+    const uint32_t x0 = (key >> 16) & 15u, y0 = (key >> 20) & 15u, x1 = (key >> 24) & 15u, y1 = (key >> 28) & 15u;
+    const uint32_t cm = ((1u << x1) - 1u) & ~((1u << x0) - 1u);      // columns, 8 bits
+    const uint32_t rm = ((1u << y1) - 1u) & ~((1u << y0) - 1u);      // rows, 8 bits
+    // the row bits are spread to the byte LSBs, times the column mask
+    const uint32_t lo = cm * (((rm & 15u) * 0x00204081u) & 0x01010101u);
+    const uint32_t hi = cm * (((rm >> 4) * 0x00204081u) & 0x01010101u);
+    return make_uint4(lo, hi, id, 0u);
+}
+
+// MODE 0: stage both tile halves; 1: only tiles 0-31; 2: only tiles 32-63; 3: direct global stores (no staging)
+template <int MODE>
+__device__ __forceinline__ void scatter_walk(const UnitInfo& ui, const uint32_t* __restrict__ keys,
+                                             const uint32_t* __restrict__ vals, uint4* s_item, int lane, uint32_t a0,
+                                             uint32_t a1, uint32_t* __restrict__ point_list) {
+    const uint32_t bit = 1u << lane;
+    uint32_t key = 0, id = 0;
+    if ((uint32_t)lane < ui.count) { key = keys[ui.first + lane]; id = vals[ui.first + lane]; }
+    for (uint32_t base = 0; base < ui.count; base += 32) {
+        const int nitems = (int)min(32u, ui.count - base);
+        __syncwarp();
+        s_item[lane] = item_record(key, id);
+        __syncwarp();
+        // next batch's loads fly while this batch is appended
+        const uint32_t nxt = base + 32 + lane;
+        if (nxt < ui.count) { key = keys[ui.first + nxt]; id = vals[ui.first + nxt]; }
+#pragma unroll 4
+        for (int i = 0; i < nitems; ++i) {
+            const uint4 it = s_item[i];
+            if (MODE == 0 || MODE == 1) sts_append(a0, it.z, it.x & bit);
+            if (MODE == 0 || MODE == 2) sts_append(a1, it.z, it.y & bit);
+            if (MODE == 3) {
+                if (it.x & bit) point_list[a0++] = it.z;
+                if (it.y & bit) point_list[a1++] = it.z;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// copy the staged runs of one tile half to the tile lists: two tiles per iteration, one per half warp
+__device__ __forceinline__ void scatter_copy_out(const uint32_t* q, uint32_t len, uint32_t off, uint32_t pos, int lane,
+                                                 uint32_t* __restrict__ point_list) {
+    unsigned live = __ballot_sync(0xFFFFFFFFu, len != 0);
+    const int sub = lane & 15;
+    while (live) {
+        const int ta = __ffs(live) - 1;
+        live &= live - 1;
+        const int tb = live ? __ffs(live) - 1 : -1;
+        live &= live - 1;
+        const int mine = lane < 16 ? ta : tb;
+        const int src_lane = mine < 0 ? 0 : mine;
+        uint32_t c = __shfl_sync(0xFFFFFFFFu, len, src_lane);
+        const uint32_t o = __shfl_sync(0xFFFFFFFFu, off, src_lane);
+        const uint32_t p = __shfl_sync(0xFFFFFFFFu, pos, src_lane);
+        if (mine < 0) c = 0;
+        for (uint32_t e = sub; e < c; e += 16) point_list[p + e] = q[o + e];
+    }
 }
 
 __global__ void __launch_bounds__(SQ_WARPS * 32) cell_scatter_staged_kernel(
@@ -299,8 +360,8 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) cell_scatter_staged_kernel(
         pos[h] = p;
         len[h] = l;
     }
-    // staging slice of every tile: exclusive scan of the run lengths in tile order (0..31, then 32..63)
-    uint32_t off[2];
+    // staging slice of every tile: exclusive scan of the run lengths inside each half (tiles 0..31, 32..63)
+    uint32_t off[2], tot[2];
     {
         uint32_t x0 = len[0], x1 = len[1];
 #pragma unroll
@@ -308,61 +369,28 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) cell_scatter_staged_kernel(
             const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, x0, o), y1 = __shfl_up_sync(0xFFFFFFFFu, x1, o);
             if (lane >= o) { x0 += y0; x1 += y1; }
         }
-        const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
+        tot[0] = __shfl_sync(0xFFFFFFFFu, x0, 31);
+        tot[1] = __shfl_sync(0xFFFFFFFFu, x1, 31);
         off[0] = x0 - len[0];
-        off[1] = tot0 + x1 - len[1];
+        off[1] = x1 - len[1];
     }
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, off[1] + len[1], 31);
-    const bool staged = total <= (uint32_t)SQ_ENTRIES;     // warp-uniform
-    const uint32_t bit = 1u << lane;
-    // append cursors: byte addresses in the staging buffer when staged, list positions otherwise
     const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(q);
-    uint32_t a0 = q_addr + 4u * off[0], a1 = q_addr + 4u * off[1];
-    uint32_t cur0 = pos[0], cur1 = pos[1];
-
-    for (uint32_t base = 0; base < ui.count; base += 32) {
-        const int nitems = (int)min(32u, ui.count - base);
-        if (lane < nitems) {
-            const uint32_t key = keys[ui.first + base + lane];
-            const uint32_t x0 = (key >> 16) & 15u, y0 = (key >> 20) & 15u, x1 = (key >> 24) & 15u, y1 = (key >> 28) & 15u;
-            const uint32_t cm = ((1u << x1) - 1u) & ~((1u << x0) - 1u);      // columns, 8 bits
-            const uint32_t rm = ((1u << y1) - 1u) & ~((1u << y0) - 1u);      // rows, 8 bits
-            // coverage bit (8 y + x): the row bits are spread to the byte LSBs, times the column mask
-            const uint32_t lo = cm * (((rm & 15u) * 0x00204081u) & 0x01010101u);
-            const uint32_t hi = cm * (((rm >> 4) * 0x00204081u) & 0x01010101u);
-            s_item[lane] = make_uint4(lo, hi, vals[ui.first + base + lane], 0u);
-        }
+    // all branches below are warp-uniform
+    if (tot[0] + tot[1] <= (uint32_t)SQ_ENTRIES) {
+        off[1] += tot[0];
+        scatter_walk<0>(ui, keys, vals, s_item, lane, q_addr + 4u * off[0], q_addr + 4u * off[1], point_list);
+        scatter_copy_out(q, len[0], off[0], pos[0], lane, point_list);
+        scatter_copy_out(q, len[1], off[1], pos[1], lane, point_list);
+    } else if (max(tot[0], tot[1]) <= (uint32_t)SQ_ENTRIES) {
+        // two walks over the unit's items, one tile half each
+        scatter_walk<1>(ui, keys, vals, s_item, lane, q_addr + 4u * off[0], 0u, point_list);
+        scatter_copy_out(q, len[0], off[0], pos[0], lane, point_list);
         __syncwarp();
-        if (staged) {
-#pragma unroll 4
-            for (int i = 0; i < nitems; ++i) {
-                const uint4 it = s_item[i];
-                sts_append(a0, it.z, it.x & bit);
-                sts_append(a1, it.z, it.y & bit);
-            }
-        } else {
-#pragma unroll 4
-            for (int i = 0; i < nitems; ++i) {
-                const uint4 it = s_item[i];
-                if (it.x & bit) point_list[cur0++] = it.z;
-                if (it.y & bit) point_list[cur1++] = it.z;
-            }
-        }
-        __syncwarp();
-    }
-    if (!staged) return;
-    // copy the runs out, one tile after the other, 32 consecutive entries per store instruction
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        unsigned live = __ballot_sync(0xFFFFFFFFu, len[h] != 0);
-        while (live) {
-            const int t = __ffs(live) - 1;
-            live &= live - 1;
-            const uint32_t c = __shfl_sync(0xFFFFFFFFu, len[h], t);
-            const uint32_t* src = q + __shfl_sync(0xFFFFFFFFu, off[h], t);
-            uint32_t* out = point_list + __shfl_sync(0xFFFFFFFFu, pos[h], t);
-            for (uint32_t e = lane; e < c; e += 32) out[e] = src[e];
-        }
+        scatter_walk<2>(ui, keys, vals, s_item, lane, 0u, q_addr + 4u * off[1], point_list);
+        scatter_copy_out(q, len[1], off[1], pos[1], lane, point_list);
+    } else {
+        // very large splats: the unit's output does not fit the staging buffer
+        scatter_walk<3>(ui, keys, vals, s_item, lane, pos[0], pos[1], point_list);
     }
 }
 

@@ -307,6 +307,212 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(cons
     }
 }
 
+// ---- packed variant: 2 pixels per lane, their arithmetic paired in Blackwell's 2-wide fp32 instructions ------
+// sm_100 adds FADD2 / FMUL2 / FFMA2 (PTX add/mul/fma.rn.f32x2): one issue slot performs the operation on a pair of
+// fp32 values held in an aligned register pair.  The composite kernels are bound by instruction issue (ncu: 85 %
+// issue-active, < 3 % DRAM), so pairing the two pixels of a lane halves the issue cost of the floating-point part.
+// IEEE rounding per element is that of the scalar instruction: the expression shapes that decide which pairs blend
+// (power, alpha; forward.cu:353-368) are the same trees as in the scalar kernel, fused exactly where nvcc fuses them.
+// Per-Gaussian operands are staged in shared memory already duplicated ({x, x, y, y} ...) so that one LDS.128 yields
+// two ready-made broadcast pairs and no register moves are needed.
+struct __align__(16) PairRec {      // 80 bytes per staged Gaussian
+    float4 xy;     // {x, x, y, y}
+    float4 ac;     // {conic.x, conic.x, conic.z, conic.z}
+    float4 bo;     // {-conic.y, -conic.y, opacity, opacity}
+    float4 rg;     // {r, r, g, g}
+    float4 bk;     // {b, b, |opacity| W/2, |opacity| H/2}
+};
+
+__device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
+
+__global__ void __launch_bounds__(128) render_bwd_packed_kernel(const __grid_constant__ RenderBwdParams p) {
+    using PM = PixelMap<2>;
+    constexpr int THREADS = PM::THREADS;   // 128
+    constexpr int WARPS = PM::WARPS;       // 4
+    constexpr int PB = 128;                // instances staged per round (one per thread)
+    __shared__ uint32_t s_id[PB];
+    __shared__ __align__(16) float4 s_geo[PB];    // {x, y, hx, hy} for the per-warp culling
+    __shared__ PairRec s_rec[PB];
+    __shared__ __align__(16) float s_acc[PB][RB_ACC];
+    __shared__ uint32_t s_max[WARPS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + p.ty0;
+    const size_t plane = (size_t)p.H * p.W;
+    const float bg0 = p.bg[0], bg1 = p.bg[1], bg2 = p.bg[2];
+
+    // per-pixel state, pixel 0 in .x and pixel 1 in .y of every pair
+    float2 npx, npy, T, Tb, rdot, last_cd, last_alpha, dL0, dL1, dL2;
+    uint32_t last_contributor[2];
+    float bx0 = 3.0e38f, bx1 = -3.0e38f, by0 = 3.0e38f, by1 = -3.0e38f;
+    {
+        float px[2], py[2], t[2], tb[2], d0[2], d1[2], d2[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            int lx, ly;
+            PM::pixel(tid, k, lx, ly);
+            const unsigned ux = tile_x * TILE + lx, uy = tile_y * TILE + ly;
+            const unsigned pix_id = p.W * uy + ux;
+            const bool inside = ux < (unsigned)p.W && uy < (unsigned)p.H;
+            px[k] = (float)ux; py[k] = (float)uy;
+            t[k] = 0.f; d0[k] = d1[k] = d2[k] = 0.f;
+            last_contributor[k] = 0;
+            if (inside) {
+                const float2 so = p.subpixel_offset[pix_id];
+                px[k] += so.x; py[k] += so.y;
+                t[k] = p.final_T[pix_id];
+                last_contributor[k] = p.n_contrib[pix_id];
+                d0[k] = p.dL_dpix[pix_id]; d1[k] = p.dL_dpix[plane + pix_id]; d2[k] = p.dL_dpix[2 * plane + pix_id];
+                bx0 = fminf(bx0, px[k]); bx1 = fmaxf(bx1, px[k]);
+                by0 = fminf(by0, py[k]); by1 = fmaxf(by1, py[k]);
+            }
+            tb[k] = -t[k] * (bg0 * d0[k] + bg1 * d1[k] + bg2 * d2[k]);
+        }
+        npx = make_float2(-px[0], -px[1]); npy = make_float2(-py[0], -py[1]);
+        T = make_float2(t[0], t[1]); Tb = make_float2(tb[0], tb[1]);
+        dL0 = make_float2(d0[0], d0[1]); dL1 = make_float2(d1[0], d1[1]); dL2 = make_float2(d2[0], d2[1]);
+        rdot = last_cd = last_alpha = make_float2(0.f, 0.f);
+    }
+    const WarpBox box = warp_box_reduce(bx0, bx1, by0, by1);
+    const uint2 range = p.ranges[tile_y * p.grid_x + tile_x];
+
+    const uint32_t warp_last = __reduce_max_sync(0xFFFFFFFFu, max(last_contributor[0], last_contributor[1]));
+    if (lane == 0) s_max[warp] = warp_last;
+    __syncthreads();
+    uint32_t tile_last = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) tile_last = max(tile_last, s_max[w]);
+    const int total = (int)min(tile_last, range.y - range.x);
+    const int rounds = (total + PB - 1) / PB;
+
+    const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
+    const float2 mhalf = make_float2(-0.5f, -0.5f), one = make_float2(1.f, 1.f);
+
+    int my_slot;
+    {
+        float dummy[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) dummy[q] = 0.f;
+        my_slot = butterfly10(dummy, lane);
+    }
+    const bool slot_owner = (lane & 1) == 0 && my_slot < 10;
+
+    int toDo = total;
+    for (int r = 0; r < rounds; ++r, toDo -= PB) {
+        __syncthreads();
+        {
+            const int progress = r * PB + tid;
+            if (progress < total) {
+                const uint32_t id = p.point_list[range.x + total - progress - 1];
+                s_id[tid] = id;
+                const float4* src = p.rec + 2 * (size_t)id;
+                const float4 g = src[0], c = src[1];
+                const float* col = p.colors + 3 * (size_t)id;
+                const float cr = col[0], cg = col[1], cb = col[2];
+                s_geo[tid] = g;
+                PairRec rec;
+                rec.xy = make_float4(g.x, g.x, g.y, g.y);
+                rec.ac = make_float4(c.x, c.x, c.z, c.z);
+                rec.bo = make_float4(-c.y, -c.y, c.w, c.w);
+                rec.rg = make_float4(cr, cr, cg, cg);
+                rec.bk = make_float4(cb, cb, fabsf(c.w) * ddelx_dx, fabsf(c.w) * ddely_dy);
+                s_rec[tid] = rec;
+            }
+            float4* a = reinterpret_cast<float4*>(s_acc[tid]);
+            a[0] = a[1] = a[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+
+        const int n = min(PB, toDo);
+        const int first_pos = total - 1 - r * PB;
+
+#pragma unroll 1
+        for (int w = 0; w < PB / 32; ++w) {
+            const int jl = w * 32 + lane;
+            const bool rel = jl < n && (uint32_t)(first_pos - jl) < warp_last && box_may_touch(s_geo[jl], box);
+            unsigned mm = __ballot_sync(0xFFFFFFFFu, rel);
+            while (mm) {
+                const int j = w * 32 + __ffs(mm) - 1;
+                mm &= mm - 1;
+                const uint32_t pos = (uint32_t)(first_pos - j);
+                const PairRec& R = s_rec[j];
+                const float4 xy = R.xy, ac = R.ac, bo = R.bo;
+
+                // power = -0.5 (A dx dx + C dy dy) - B dx dy, contracted as nvcc contracts the scalar expression:
+                //   s = fma(dx, A dx, (C dy) dy);  power = fma(s, -0.5, -((B dx) dy))      (checked against the SASS)
+                const float2 dx = __fadd2_rn(lo2(xy), npx), dy = __fadd2_rn(hi2(xy), npy);
+                const float2 t1 = __fmul2_rn(lo2(ac), dx);
+                const float2 t3 = __fmul2_rn(dy, __fmul2_rn(hi2(ac), dy));
+                const float2 un = __fmul2_rn(dy, __fmul2_rn(lo2(bo), dx));       // -(B dx) dy
+                const float2 power = __ffma2_rn(__ffma2_rn(dx, t1, t3), mhalf, un);
+                const float g0 = expf(power.x), g1 = expf(power.y);
+                const float2 oG = __fmul2_rn(hi2(bo), make_float2(g0, g1));
+                const float a0 = min(0.99f, oG.x), a1 = min(0.99f, oG.y);
+                const bool act0 = pos < last_contributor[0] && !(power.x > 0.0f) && !(a0 < 1.0f / 255.0f);
+                const bool act1 = pos < last_contributor[1] && !(power.y > 0.0f) && !(a1 < 1.0f / 255.0f);
+                if (!__any_sync(0xFFFFFFFFu, act0 || act1)) continue;   // warp-uniform
+                // pairs that do not blend run through the arithmetic as G = alpha = 0 (see the scalar kernel)
+                const float2 G = make_float2(act0 ? g0 : 0.f, act1 ? g1 : 0.f);
+                const float2 alpha = make_float2(act0 ? a0 : 0.f, act1 ? a1 : 0.f);
+
+                const float4 rg = R.rg, bk = R.bk;
+                const float2 oma = __fadd2_rn(one, make_float2(-alpha.x, -alpha.y));
+                const float2 inv = make_float2(rcp_approx(oma.x), rcp_approx(oma.y));
+                T = __fmul2_rn(T, inv);
+                const float2 aT = __fmul2_rn(alpha, T);
+                rdot = __ffma2_rn(last_alpha, __fadd2_rn(last_cd, make_float2(-rdot.x, -rdot.y)), rdot);
+                const float2 cd = __ffma2_rn(lo2(bk), dL2, __ffma2_rn(hi2(rg), dL1, __fmul2_rn(lo2(rg), dL0)));
+                last_cd = cd;
+                last_alpha = alpha;
+                const float2 dL_dalpha = __ffma2_rn(__fadd2_rn(cd, make_float2(-rdot.x, -rdot.y)), T, __fmul2_rn(Tb, inv));
+                const float2 wgt = __fmul2_rn(G, dL_dalpha);
+                const float2 wx = __fmul2_rn(wgt, dx), wy = __fmul2_rn(wgt, dy);
+                // t1 = A wx + B wy, t2 = C wy + B wx  (lo2(bo) holds -B: the sign disappears under |.|)
+                const float2 q1 = __ffma2_rn(lo2(bo), wy, make_float2(-0.f, -0.f));   // -B wy
+                const float2 u1 = __ffma2_rn(lo2(ac), wx, make_float2(-q1.x, -q1.y));
+                const float2 q2 = __fmul2_rn(lo2(bo), wx);                             // -B wx
+                const float2 u2 = __ffma2_rn(hi2(ac), wy, make_float2(-q2.x, -q2.y));
+                const float2 mxx = __fmul2_rn(wx, dx), mxy = __fmul2_rn(wx, dy), myy = __fmul2_rn(wy, dy);
+                const float2 c0 = __fmul2_rn(aT, dL0), c1 = __fmul2_rn(aT, dL1), c2 = __fmul2_rn(aT, dL2);
+                float v[10];
+                v[0] = wx.x + wx.y;
+                v[1] = wy.x + wy.y;
+                v[2] = fmaf(fabsf(u2.x), bk.w, fabsf(u1.x) * bk.z) + fmaf(fabsf(u2.y), bk.w, fabsf(u1.y) * bk.z);
+                v[3] = mxx.x + mxx.y;
+                v[4] = mxy.x + mxy.y;
+                v[5] = myy.x + myy.y;
+                v[6] = wgt.x + wgt.y;
+                v[7] = c0.x + c0.y;
+                v[8] = c1.x + c1.y;
+                v[9] = c2.x + c2.y;
+                butterfly10(v, lane);
+                if (slot_owner) atomicAdd(&s_acc[j][my_slot], v[0]);
+            }
+        }
+        __syncthreads();
+        if (tid < n) {
+            const float* a = s_acc[tid];
+            const float4 a0 = *reinterpret_cast<const float4*>(a);
+            const float4 a1 = *reinterpret_cast<const float4*>(a + 4);
+            const float4 a2 = *reinterpret_cast<const float4*>(a + 8);
+            const bool any = (a0.x != 0.f) | (a0.y != 0.f) | (a0.z != 0.f) | (a0.w != 0.f) | (a1.x != 0.f) |
+                             (a1.y != 0.f) | (a1.z != 0.f) | (a1.w != 0.f) | (a2.x != 0.f) | (a2.y != 0.f);
+            if (any) {
+                const PairRec& R = s_rec[tid];
+                const float A = R.ac.x, C = R.ac.z, B = -R.bo.x, o = R.bo.z;
+                const float gx = -o * ddelx_dx * (A * a0.x + B * a0.y);
+                const float gy = -o * ddely_dy * (C * a0.y + B * a0.x);
+                const float h = -0.5f * o;
+                float* dst = p.accum + (size_t)s_id[tid] * RB_ACC;
+                red_add_v4(dst + 0, gx, gy, a0.z, h * a0.w);
+                red_add_v4(dst + 4, h * a1.x, h * a1.y, a1.z, a1.w);
+                red_add_v4(dst + 8, a2.x, a2.y, 0.f, 0.f);
+            }
+        }
+    }
+}
+
 #ifndef GSR_BWD_PPT
 #define GSR_BWD_PPT 2     // default pixels per thread; GSR_BWD_PPT in the environment overrides (tuning aid)
 #endif
@@ -332,6 +538,16 @@ int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinSta
     p.accum = reinterpret_cast<float*>(accum);
     if (ty1 <= ty0) return 0;
     dim3 grid(p.grid_x, ty1 - ty0, 1);
+    static int packed = -1;
+    if (packed < 0) {
+        const char* e = getenv("GSR_BWD_PACKED");     // tuning aid: 1 = 2 pixels/lane in paired fp32 instructions
+        packed = e ? atoi(e) : 1;
+    }
+    if (packed) {
+        render_bwd_packed_kernel<<<grid, 128, 0, s>>>(p);
+        count_launches(1);
+        return 0;
+    }
     switch (bwd_ppt()) {
         case 1: render_bwd_kernel<1><<<grid, PixelMap<1>::THREADS, 0, s>>>(p); break;
         case 4: render_bwd_kernel<4><<<grid, PixelMap<4>::THREADS, 0, s>>>(p); break;
