@@ -324,6 +324,9 @@ def main():
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
     import parallel
     line["impl"] = "ours"
+    # every timed step is a FULL forward (projection + binning + composite): the geometry reuse between consecutive
+    # calls on identical tensors is switched off here and measured separately ("two_pass" below)
+    _C.set_geometry_cache(False)
     bands = None
     if world > 1:
         rows = (H + 15) // 16
@@ -412,6 +415,25 @@ def main():
     else:
         line["stages"] = {k: {"ms": v} for k, v in stage_ms.items()}
         line["bands"] = bands
+
+    # wild-gaussians' step composites the same Gaussians twice (raw + appearance-toned colours,
+    # method.py:1573-1611): two forwards + two backwards, with and without reuse of the first pass's geometry/binning
+    if world == 1:
+        d2 = dict(d); d2["colors_precomp"] = (1.0 - d["colors_precomp"]).contiguous() if "colors_precomp" in d else None
+        if d2["colors_precomp"] is not None:
+            def two_pass():
+                _C.clear_geometry_cache()
+                f1 = _C.rasterize_gaussians(*call_args(d))
+                f2 = _C.rasterize_gaussians(*call_args(d2))
+                _C.rasterize_gaussians_backward_lean(*backward_args(d2, f2[2], f2[3], f2[0], f2[4], f2[5]))
+                _C.rasterize_gaussians_backward_lean(*backward_args(d, f1[2], f1[3], f1[0], f1[4], f1[5]))
+            tp = {}
+            for name, on in (("ms_reuse_geometry", True), ("ms_independent_passes", False)):
+                _C.set_geometry_cache(on)
+                tp[name] = time_steps(two_pass, max(3, a.steps // 2), 3, dev, 1)
+            _C.set_geometry_cache(False)
+            tp["what"] = "2 forwards (different colours, same geometry) + 2 backwards, device-timed"
+            line["two_pass"] = tp
 
     # e2e through the public API with host buffers
     if not a.no_e2e:

@@ -169,8 +169,13 @@ def test_autograd_two_passes_like_method_py(C, dev):
     rast = GaussianRasterizer(_settings(d))
     kw = dict(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"], scales=leaves["scales"],
               rotations=leaves["rotations"], shs=None, cov3D_precomp=None)
+    C.set_geometry_cache(True)
+    C.clear_geometry_cache()
+    hits0 = C.geometry_cache_hits()
     img_a, radii, acc = rast(colors_precomp=col_a, **kw)
     img_b, radii_b, acc_b = rast(colors_precomp=col_b, **kw)
+    # the second pass reused the projection / depth order / tile lists of the first
+    assert C.geometry_cache_hits() == hits0 + 1
     assert img_a.shape == (3, 208, 320) and radii.dtype == torch.int32 and acc.shape == (208, 320)
     assert torch.equal(radii, radii_b) and torch.equal(acc, acc_b)
     (img_a * d["dL_dpix"]).sum().backward(retain_graph=True)
@@ -194,6 +199,43 @@ def test_autograd_two_passes_like_method_py(C, dev):
     assert rel_err(m2d_a.cpu().numpy(), o_a["grads"]["dL_dmeans2D"].cpu().numpy()) < GRAD_TOL
     assert rel_err(col_a.grad.cpu().numpy(), o_a["grads"]["dL_dcolors"].cpu().numpy()) < GRAD_TOL
     assert (means2D.grad[:, 2] >= 0).all()          # abs-gradient channel
+
+
+def test_geometry_cache_is_invalidated_by_in_place_updates(C, dev):
+    """The reuse keys on tensor identity + version: an optimizer-style in-place update, another tensor object, other
+    settings or a disabled cache all force a full forward; a hit gives bit-identical outputs."""
+    scene = synthetic.make_scene(P=20_000, W=256, H=160, sh_degree=None, seed=43)
+    d = synthetic.to_device(scene, dev)
+    C.set_geometry_cache(True)
+    C.clear_geometry_cache()
+    args = list(call_args(d))
+    h0 = C.geometry_cache_hits()
+    R1, c1, radii1, g1, b1, i1 = C.rasterize_gaussians(*args)
+    R2, c2, radii2, g2, b2, i2 = C.rasterize_gaussians(*args)
+    assert C.geometry_cache_hits() == h0 + 1
+    assert R1 == R2 and torch.equal(c1, c2) and torch.equal(radii1, radii2)
+    assert g2.data_ptr() == g1.data_ptr() and b2.data_ptr() == b1.data_ptr() and i2.data_ptr() != i1.data_ptr()
+    v1 = C.debug_views(g1, b1, i1, d["means3D"].shape[0], 0, 256, 160, R1)
+    v2 = C.debug_views(g2, b2, i2, d["means3D"].shape[0], 0, 256, 160, R2)
+    for k in ("final_T", "n_contrib", "ranges", "point_list"):
+        assert torch.equal(v1[k], v2[k]), k
+    # in-place update of a geometry input -> version bump -> miss, and the new result reflects the update
+    d["means3D"].mul_(1.001)
+    R3, c3, *_ = C.rasterize_gaussians(*args)
+    assert C.geometry_cache_hits() == h0 + 1
+    assert not torch.equal(c3, c1)
+    # a different colour tensor alone is a hit; a different opacity tensor object is a miss
+    args_c = list(args); args_c[2] = (1.0 - d["colors_precomp"]).contiguous()
+    C.rasterize_gaussians(*args_c)
+    assert C.geometry_cache_hits() == h0 + 2
+    args_o = list(args); args_o[3] = d["opacities"].clone()
+    C.rasterize_gaussians(*args_o)
+    assert C.geometry_cache_hits() == h0 + 2
+    C.set_geometry_cache(False)
+    C.rasterize_gaussians(*args_o)
+    C.rasterize_gaussians(*args_o)
+    assert C.geometry_cache_hits() == h0 + 2
+    C.set_geometry_cache(True)
 
 
 def test_sh_path_and_debug_flag(C, dev):

@@ -336,9 +336,11 @@ int gsr_forward_recolor(const GsrForwardArgs* a, const void* geom_buffer, const 
     const size_t T = (size_t)tiles_x(a->W) * tiles_y(a->H);
     if (im2.ranges != im.ranges)
         GSR_CUDA(cudaMemcpyAsync(im2.ranges, im.ranges, T * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
+    prof_begin(ST_RENDER_FWD, s);
     rc = launch_render_fwd(*a, g, b, im2, a->colors_precomp, ty0, ty1, s);
     if (rc) return rc;
     GSR_STAGE(s, a->debug != 0, "render_fwd_kernel(recolor)");
+    prof_end(ST_RENDER_FWD, s);
     return 0;
 }
 

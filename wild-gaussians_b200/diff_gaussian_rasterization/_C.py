@@ -108,6 +108,42 @@ def get_tile_row_shard():
     return _shard
 
 
+# ---- geometry reuse across consecutive forward calls ------------------------------------------
+# One entry (the previous forward).  An entry is reused only if every geometry input is THE SAME tensor object with
+# the same version counter (no in-place modification since), on the same stream, with the same scalar settings.
+# The entry keeps those tensors alive, so their addresses cannot be recycled for other data.  Modifying a tensor
+# behind autograd's back (``x.data.add_(...)``) does not bump the version: set GSR_GEOM_CACHE=0 for such code.
+_GEOM_CACHE_ON = os.environ.get("GSR_GEOM_CACHE", "1") != "0"
+_geom_cache: dict = {}
+
+
+def geo_key_tensors(*tensors):
+    return tuple(tensors)
+
+
+def _geometry_key(dev, stream, P, W, H, M, a, tensors):
+    return (str(dev), int(stream), P, W, H, M, float(a.scale_modifier), float(a.tan_fovx), float(a.tan_fovy),
+            float(a.kernel_size), int(a.prefiltered), int(a.debug), int(a.tile_y0), int(a.tile_y1),
+            tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors))
+
+
+def set_geometry_cache(on: bool) -> None:
+    """Enable / disable the reuse (benchmarks of a full forward switch it off)."""
+    global _GEOM_CACHE_ON
+    _GEOM_CACHE_ON = bool(on)
+    if not on:
+        _geom_cache.pop("entry", None)
+
+
+def clear_geometry_cache() -> None:
+    """Drop the cached geometry/binning state of the previous forward (frees its buffers)."""
+    _geom_cache.pop("entry", None)
+
+
+def geometry_cache_hits() -> int:
+    return int(_geom_cache.get("hits", 0))
+
+
 def _check(rc: int, what: str) -> None:
     if rc != 0:
         msg = _lib.gsr_last_error().decode("utf-8", "replace")
@@ -175,9 +211,28 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 
         gb, ib = c_size_t(0), c_size_t(0)
         _check(_lib.gsr_forward_sizes(P, M, W, H, byref(gb), byref(ib)), "gsr_forward_sizes")
+        stream = _stream(dev)
+
+        # Geometry reuse: wild-gaussians composites the SAME Gaussians two or three times per step
+        # with different colours (raw / appearance-toned / depth; method.py:1573-1631).  When every geometry input is
+        # the identical, unmodified tensor object of the previous call, projection, depth ordering and tile binning
+        # are not repeated: only the composite runs, on the previous call's geom / binning state.
+        geo_key = _geometry_key(dev, stream, P, W, H, M, a, (means3D, opacity, scales, rotations, cov3D_precomp,
+                                                              viewmatrix, projmatrix, subpixel_offset))
+        hit = _geom_cache.get("entry") if (_GEOM_CACHE_ON and M == 0) else None
+        if hit is not None and hit["key"] == geo_key and all(
+                (x is y) or (x.numel() == 0 and y.numel() == 0)      # "absent" inputs are fresh empty tensors per call
+                for x, y in zip(hit["tensors"], geo_key_tensors(means3D, opacity, scales, rotations, cov3D_precomp,
+                                                                viewmatrix, projmatrix, subpixel_offset))):
+            img2 = torch.empty((ib.value,), **byte)
+            a.radii = hit["radii"].data_ptr()
+            _check(_lib.gsr_forward_recolor(byref(a), hit["geom"].data_ptr(), hit["binning"].data_ptr(),
+                                            hit["img"].data_ptr(), img2.data_ptr(), stream), "gsr_forward_recolor")
+            _geom_cache["hits"] = _geom_cache.get("hits", 0) + 1
+            return hit["R"], out_color, hit["radii"].clone(), hit["geom"], hit["binning"], img2
+
         geom = torch.empty((gb.value,), **byte)
         img = torch.empty((ib.value,), **byte)
-        stream = _stream(dev)
         R, N1 = c_int(0), c_int(0)
         _check(_lib.gsr_forward_geometry(byref(a), geom.data_ptr(), img.data_ptr(), stream, byref(R), byref(N1)),
                "gsr_forward_geometry")
@@ -190,6 +245,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         # `scratch` goes back to torch's stream-ordered caching allocator here: any later
         # allocation on this stream is ordered after the kernels that use it.
         del scratch
+        if _GEOM_CACHE_ON and M == 0:
+            _geom_cache["entry"] = dict(key=geo_key, tensors=geo_key_tensors(means3D, opacity, scales, rotations,
+                                                                               cov3D_precomp, viewmatrix, projmatrix,
+                                                                               subpixel_offset),
+                                        R=R.value, radii=radii, geom=geom, binning=binning, img=img)
     return R.value, out_color, radii, geom, binning, img
 
 
