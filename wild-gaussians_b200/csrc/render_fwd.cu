@@ -212,6 +212,174 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_fwd_kernel(cons
     }
 }
 
+// ---- packed variant: 2 pixels per lane, their arithmetic paired in FADD2 / FMUL2 / FFMA2 ---------------------
+// (see render_bwd.cu for the rationale: the composite is issue-bound; sm_100's 2-wide fp32 instructions halve the
+// issue cost of everything that is not expf / compare / select.)  Every element of a pair goes through the same
+// IEEE operations, in the same order, as the scalar kernel above -- power = fma(fma(dx, A dx, (C dy) dy), -0.5,
+// -((B dx) dy)), alpha = min(0.99, o expf(power)), test_T = T (1 - alpha), C = fma(T, alpha c, C) -- so pixels,
+// final_T and n_contrib are bit-identical.  A pair that does not blend is carried as alpha = 0, which leaves C and T
+// unchanged exactly.
+// Staging: one instance per thread and round; the raw records travel through registers (loads of round r+1 are
+// issued before round r is blended) and are written to shared memory already duplicated ({x, x, y, y}, ...), so one
+// LDS.128 yields two ready-made broadcast pairs.
+struct __align__(16) FwdPairRec {     // 80 bytes
+    float4 xy;     // {x, x, y, y}
+    float4 ac;     // {conic.x, conic.x, conic.z, conic.z}
+    float4 bo;     // {-conic.y, -conic.y, opacity, opacity}
+    float4 rg;     // {r, r, g, g}
+    float4 bb;     // {b, b, -, -}
+};
+
+__global__ void __launch_bounds__(128) render_fwd_packed_kernel(const __grid_constant__ RenderFwdParams p) {
+    using PM = PixelMap<2>;
+    constexpr int THREADS = 128;
+    constexpr int PB = 128;               // instances per round
+    __shared__ __align__(16) float4 s_geo[2][PB];      // {x, y, hx, hy} for the per-warp culling
+    __shared__ FwdPairRec s_rec[2][PB];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tile_x = blockIdx.x, tile_y = blockIdx.y + p.ty0;
+
+    float2 npx, npy;
+    unsigned pix_id[2];
+    bool inside[2];
+    bool live0 = false, live1 = false;
+    float bx0 = 3.0e38f, bx1 = -3.0e38f, by0 = 3.0e38f, by1 = -3.0e38f;
+    {
+        float px[2], py[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            int lx, ly;
+            PM::pixel(tid, k, lx, ly);
+            const unsigned ux = tile_x * TILE + lx, uy = tile_y * TILE + ly;
+            pix_id[k] = p.W * uy + ux;
+            inside[k] = ux < (unsigned)p.W && uy < (unsigned)p.H;
+            px[k] = (float)ux; py[k] = (float)uy;
+            if (inside[k]) {
+                const float2 so = p.subpixel_offset[pix_id[k]];
+                px[k] += so.x; py[k] += so.y;
+                bx0 = fminf(bx0, px[k]); bx1 = fmaxf(bx1, px[k]);
+                by0 = fminf(by0, py[k]); by1 = fmaxf(by1, py[k]);
+            }
+        }
+        live0 = inside[0]; live1 = inside[1];
+        npx = make_float2(-px[0], -px[1]); npy = make_float2(-py[0], -py[1]);
+    }
+    const WarpBox box = warp_box_reduce(bx0, bx1, by0, by1);
+
+    const uint2 range = p.ranges[tile_y * p.grid_x + tile_x];
+    const int total = (int)(range.y - range.x);
+    const int rounds = (total + PB - 1) / PB;
+
+    float2 T = make_float2(1.f, 1.f), C0 = make_float2(0.f, 0.f), C1 = C0, C2 = C0;
+    uint32_t last0 = 0, last1 = 0;
+    const float2 mhalf = make_float2(-0.5f, -0.5f), one = make_float2(1.f, 1.f);
+
+    if (rounds > 0) {
+        // raw record of the instance this thread stages next (register prefetch)
+        float4 g = make_float4(0.f, 0.f, -1.f, -1.f), c = make_float4(0.f, 0.f, 0.f, 0.f);
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        auto fetch = [&](uint32_t id, bool valid) {
+            if (valid) {
+                const float4* src = p.rec + 2 * (size_t)id;
+                g = src[0]; c = src[1];
+                const float* col = p.colors + 3 * (size_t)id;
+                cr = col[0]; cg = col[1]; cb = col[2];
+            }
+        };
+        auto id_of = [&](int round) -> uint32_t {
+            const int i = round * PB + tid;
+            return (round < rounds && i < total) ? p.point_list[range.x + i] : 0u;
+        };
+        uint32_t id_next = id_of(0);
+        fetch(id_next, tid < total);
+        id_next = id_of(1);
+
+        int toDo = total;
+        for (int r = 0; r < rounds; ++r, toDo -= PB) {
+            const int buf = r & 1;
+            // write this round's (already loaded) record, duplicated, then start the next round's loads
+            s_geo[buf][tid] = g;
+            {
+                FwdPairRec rec;
+                rec.xy = make_float4(g.x, g.x, g.y, g.y);
+                rec.ac = make_float4(c.x, c.x, c.z, c.z);
+                rec.bo = make_float4(-c.y, -c.y, c.w, c.w);
+                rec.rg = make_float4(cr, cr, cg, cg);
+                rec.bb = make_float4(cb, cb, 0.f, 0.f);
+                s_rec[buf][tid] = rec;
+            }
+            if (r + 1 < rounds) {
+                fetch(id_next, (r + 1) * PB + tid < total);
+                id_next = id_of(r + 2);
+            }
+            // the round is visible to everyone; block-wide early-out vote (forward.cu:330-332).  One barrier per
+            // round suffices: buffer `buf` is rewritten in round r+2, after the barrier of round r+1.
+            const int num_done = __syncthreads_count(!(live0 || live1));
+            if (num_done == THREADS) break;
+
+            const int n = min(PB, toDo);
+            const uint32_t round_base = (uint32_t)(r * PB);
+            if (__any_sync(0xFFFFFFFFu, live0 || live1)) {
+#pragma unroll 1
+                for (int w = 0; w < PB / 32; ++w) {
+                    const int jl = w * 32 + lane;
+                    unsigned mm = __ballot_sync(0xFFFFFFFFu, jl < n && box_may_touch(s_geo[buf][jl], box));
+                    while (mm) {
+                        const int j = w * 32 + __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const FwdPairRec& R = s_rec[buf][j];
+                        const float4 xy = R.xy, ac = R.ac, bo = R.bo;
+                        const float2 dx = __fadd2_rn(make_float2(xy.x, xy.y), npx), dy = __fadd2_rn(make_float2(xy.z, xy.w), npy);
+                        const float2 t1 = __fmul2_rn(make_float2(ac.x, ac.y), dx);
+                        const float2 t3 = __fmul2_rn(dy, __fmul2_rn(make_float2(ac.z, ac.w), dy));
+                        const float2 un = __fmul2_rn(dy, __fmul2_rn(make_float2(bo.x, bo.y), dx));     // -(B dx) dy
+                        const float2 power = __ffma2_rn(__ffma2_rn(dx, t1, t3), mhalf, un);
+                        const float2 oG = __fmul2_rn(make_float2(bo.z, bo.w), make_float2(expf(power.x), expf(power.y)));
+                        const float a0 = min(0.99f, oG.x), a1 = min(0.99f, oG.y);
+                        const float2 test_T = __fmul2_rn(T, __fadd2_rn(one, make_float2(-a0, -a1)));
+                        const bool blend0 = live0 && !(power.x > 0.0f) && !(a0 < 1.0f / 255.0f);
+                        const bool blend1 = live1 && !(power.y > 0.0f) && !(a1 < 1.0f / 255.0f);
+                        const bool stop0 = blend0 && test_T.x < 0.0001f, stop1 = blend1 && test_T.y < 0.0001f;
+                        live0 = live0 && !stop0;
+                        live1 = live1 && !stop1;
+                        const bool upd0 = blend0 && !stop0, upd1 = blend1 && !stop1;
+                        if (!__any_sync(0xFFFFFFFFu, upd0 || upd1)) continue;
+                        const float2 alpha = make_float2(upd0 ? a0 : 0.f, upd1 ? a1 : 0.f);
+                        const float4 rg = R.rg, bb = R.bb;
+                        C0 = __ffma2_rn(T, __fmul2_rn(alpha, make_float2(rg.x, rg.y)), C0);
+                        C1 = __ffma2_rn(T, __fmul2_rn(alpha, make_float2(rg.z, rg.w)), C1);
+                        C2 = __ffma2_rn(T, __fmul2_rn(alpha, make_float2(bb.x, bb.y)), C2);
+                        T = make_float2(upd0 ? test_T.x : T.x, upd1 ? test_T.y : T.y);
+                        // 1-based position of this instance in the tile's list (forward.cu:349,382)
+                        const uint32_t idx = round_base + (uint32_t)j + 1u;
+                        last0 = upd0 ? idx : last0;
+                        last1 = upd1 ? idx : last1;
+                    }
+                    if (!__any_sync(0xFFFFFFFFu, live0 || live1)) break;
+                }
+            }
+        }
+    }
+
+    const size_t plane = (size_t)p.H * p.W;
+    const float bg0 = p.bg[0], bg1 = p.bg[1], bg2 = p.bg[2];
+    if (inside[0]) {
+        p.final_T[pix_id[0]] = T.x;
+        p.n_contrib[pix_id[0]] = last0;
+        p.out_color[0 * plane + pix_id[0]] = C0.x + T.x * bg0;
+        p.out_color[1 * plane + pix_id[0]] = C1.x + T.x * bg1;
+        p.out_color[2 * plane + pix_id[0]] = C2.x + T.x * bg2;
+    }
+    if (inside[1]) {
+        p.final_T[pix_id[1]] = T.y;
+        p.n_contrib[pix_id[1]] = last1;
+        p.out_color[0 * plane + pix_id[1]] = C0.y + T.y * bg0;
+        p.out_color[1 * plane + pix_id[1]] = C1.y + T.y * bg1;
+        p.out_color[2 * plane + pix_id[1]] = C2.y + T.y * bg2;
+    }
+}
+
 #ifndef GSR_FWD_PPT
 #define GSR_FWD_PPT 1     // default pixels per thread; GSR_FWD_PPT in the environment overrides (tuning aid)
 #endif
@@ -236,6 +404,16 @@ int launch_render_fwd(const GsrForwardArgs& a, const GeomState& g, const BinStat
     p.final_T = im.final_T; p.n_contrib = im.n_contrib; p.out_color = a.out_color;
     if (ty1 <= ty0) return 0;
     dim3 grid(p.grid_x, ty1 - ty0, 1);
+    static int packed = -1;
+    if (packed < 0) {
+        const char* e = getenv("GSR_FWD_PACKED");     // tuning aid: 1 = 2 pixels/lane in paired fp32 instructions
+        packed = e ? atoi(e) : 1;
+    }
+    if (packed) {
+        render_fwd_packed_kernel<<<grid, 128, 0, s>>>(p);
+        count_launches(1);
+        return 0;
+    }
     static int flat = -1;
     if (flat < 0) {
         const char* e = getenv("GSR_FWD_FLAT");      // tuning aid: 1 = predicated (branch-light) blend loop
