@@ -326,8 +326,7 @@ struct __align__(16) PairRec {      // 80 bytes per staged Gaussian
 __device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
 
-template <bool PREFETCH, int MIN_CTAS>
-__global__ void __launch_bounds__(128, MIN_CTAS) render_bwd_packed_kernel(const __grid_constant__ RenderBwdParams p) {
+__global__ void __launch_bounds__(128) render_bwd_packed_kernel(const __grid_constant__ RenderBwdParams p) {
     using PM = PixelMap<2>;
     constexpr int THREADS = PM::THREADS;   // 128
     constexpr int WARPS = PM::WARPS;       // 4
@@ -399,30 +398,18 @@ __global__ void __launch_bounds__(128, MIN_CTAS) render_bwd_packed_kernel(const 
     }
     const bool slot_owner = (lane & 1) == 0 && my_slot < 10;
 
-    // raw record of the instance this thread stages next: the global gather of round r+1 is issued before round r
-    // is processed (register prefetch), so its latency is covered by the blending
-    uint32_t id_cur = 0;
-    float4 g = make_float4(0.f, 0.f, -1.f, -1.f), c = make_float4(0.f, 0.f, 0.f, 0.f);
-    float cr = 0.f, cg = 0.f, cb = 0.f;
-    auto fetch = [&](int round) {
-        const int progress = round * PB + tid;
-        if (round < rounds && progress < total) {
-            id_cur = p.point_list[range.x + total - progress - 1];
-            const float4* src = p.rec + 2 * (size_t)id_cur;
-            g = src[0]; c = src[1];
-            const float* col = p.colors + 3 * (size_t)id_cur;
-            cr = col[0]; cg = col[1]; cb = col[2];
-        }
-    };
-    if (PREFETCH) fetch(0);
-
     int toDo = total;
     for (int r = 0; r < rounds; ++r, toDo -= PB) {
         __syncthreads();
         {
-            if (!PREFETCH) fetch(r);
-            if (r * PB + tid < total) {
-                s_id[tid] = id_cur;
+            const int progress = r * PB + tid;
+            if (progress < total) {
+                const uint32_t id = p.point_list[range.x + total - progress - 1];
+                s_id[tid] = id;
+                const float4* src = p.rec + 2 * (size_t)id;
+                const float4 g = src[0], c = src[1];
+                const float* col = p.colors + 3 * (size_t)id;
+                const float cr = col[0], cg = col[1], cb = col[2];
                 s_geo[tid] = g;
                 PairRec rec;
                 rec.xy = make_float4(g.x, g.x, g.y, g.y);
@@ -435,7 +422,6 @@ __global__ void __launch_bounds__(128, MIN_CTAS) render_bwd_packed_kernel(const 
             float4* a = reinterpret_cast<float4*>(s_acc[tid]);
             a[0] = a[1] = a[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (PREFETCH) fetch(r + 1);
         __syncthreads();
 
         const int n = min(PB, toDo);
@@ -558,14 +544,7 @@ int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinSta
         packed = e ? atoi(e) : 1;
     }
     if (packed) {
-        static int minb = -1;
-        if (minb < 0) {
-            const char* e = getenv("GSR_BWD_MINB");   // tuning aid: resident CTAs per SM the register allocation targets
-            minb = e ? atoi(e) : 9;
-        }
-        if (packed == 2) render_bwd_packed_kernel<true, 7><<<grid, 128, 0, s>>>(p);     // + register prefetch of the gather
-        else if (minb >= 10) render_bwd_packed_kernel<false, 10><<<grid, 128, 0, s>>>(p);
-        else render_bwd_packed_kernel<false, 9><<<grid, 128, 0, s>>>(p);
+        render_bwd_packed_kernel<<<grid, 128, 0, s>>>(p);
         count_launches(1);
         return 0;
     }
