@@ -81,6 +81,10 @@ REF_SCENES = [
     dict(P=20_000, W=640, H=360, sh_degree=None, seed=24, scale_range=(0.05, 0.5)),       # huge splats
     dict(P=100_000, W=512, H=512, sh_degree=None, seed=25, normalize_rot=False),
     dict(P=60_000, W=400, H=300, sh_degree=None, seed=26, cov3D_precomp=True),
+    # more than 256 binning cells (8x8 tiles each): the coarse-item sort needs two radix passes
+    dict(P=150_000, W=4096, H=2304, sh_degree=None, seed=27),
+    # medium-to-large splats: binning units whose output exceeds the staging buffer (two-walk / direct scatter paths)
+    dict(P=100_000, W=1280, H=720, sh_degree=None, seed=28, scale_range=(0.01, 0.15)),
 ]
 
 

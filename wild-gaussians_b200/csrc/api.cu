@@ -80,6 +80,8 @@ size_t carve_geom(char* base, int P, int M, GeomState* out) {
     take(cur, g.val_a, n);
     take(cur, g.val_b, n);
     g.order = g.val_a;   // 32 key bits = 4 passes (even): the sorted pairs end up in (key_a, val_a)
+    take(cur, g.cells_sorted, n);
+    take(cur, g.rect_sorted, n);
     take(cur, g.offsets, n + 1);
     g.radix_tmp_count = radix_tmp_elems(n) + scan_tmp_elems(n);
     take(cur, g.radix_tmp, g.radix_tmp_count);
@@ -231,22 +233,33 @@ int gsr_forward_geometry(const GsrForwardArgs* a, void* geom_buffer, void* img_b
     // front-to-back order of the Gaussians: stable sort on the depth bits (all 32, u32 compare
     // like the reference's key, rasterizer_impl.cu:104); culled ones carry 0xFFFFFFFF.
     prof_begin(ST_DEPTH_SORT, s);
-    rc = radix_sort_pairs(g.key_a, g.val_a, g.key_b, g.val_b, (size_t)a->P, 0, 32, g.radix_tmp, s, dbg);
+    // the last pass also gathers cells_touched and the tile rectangles into depth order (own arrays: the pass
+    // reads key_b / val_b and writes key_a / val_a, nothing may alias those while it runs)
+    RadixAux aux;
+    aux.in32 = g.cells_touched;
+    aux.out32 = g.cells_sorted;
+    aux.in64 = reinterpret_cast<const uint2*>(g.rect);
+    aux.out64 = reinterpret_cast<uint2*>(g.rect_sorted);
+    rc = radix_sort_pairs(g.key_a, g.val_a, g.key_b, g.val_b, (size_t)a->P, 0, 32, g.radix_tmp, s, dbg, &aux);
     if (rc) return rc;
     prof_end(ST_DEPTH_SORT, s);
 
     // coarse-item offsets in depth order; offsets[P] = number of coarse items
     prof_begin(ST_OFFSET_SCAN, s);
-    rc = scan_gathered(g.cells_touched, g.order, g.offsets, (size_t)a->P, g.radix_tmp + radix_tmp_elems((size_t)a->P), s);
+    rc = scan_gathered(g.cells_sorted, nullptr, g.offsets, (size_t)a->P, g.radix_tmp + radix_tmp_elems((size_t)a->P), s);
     if (rc) return rc;
     GSR_STAGE(s, dbg, "scan_gathered");
     prof_end(ST_OFFSET_SCAN, s);
 
-    uint32_t N1 = 0;
-    int32_t counters[8];
-    GSR_CUDA(cudaMemcpyAsync(&N1, g.offsets + a->P, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    GSR_CUDA(cudaMemcpyAsync(counters, g.counters, sizeof(counters), cudaMemcpyDeviceToHost, s));
+    // read-back of the counts through a small pinned buffer (a pageable destination makes the copies synchronous
+    // staging copies); one buffer per host thread, never freed
+    static thread_local int32_t* h_counts = nullptr;
+    if (!h_counts) GSR_CUDA(cudaHostAlloc((void**)&h_counts, 16 * sizeof(int32_t), cudaHostAllocDefault));
+    GSR_CUDA(cudaMemcpyAsync(h_counts + 8, g.offsets + a->P, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA(cudaMemcpyAsync(h_counts, g.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     GSR_CUDA(cudaStreamSynchronize(s));
+    const int32_t* counters = h_counts;
+    const uint32_t N1 = (uint32_t)h_counts[8];
     if (counters[0] != 0) {
         set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
         return GSR_E_PREFILTERED;

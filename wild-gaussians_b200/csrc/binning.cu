@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(int P, int cells_x, con
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // position in depth order
     if (i >= P) return;
     const uint32_t g = order[i];
-    const TileRect r = rect[g];
+    const TileRect r = rect[i];      // rectangles arrive in depth order (gathered by the last sort pass)
     if (r.x1 <= r.x0 || r.y1 <= r.y0) return;
     uint32_t off = offsets[i];
     const int cx0 = r.x0 / CELL, cx1 = (r.x1 - 1) / CELL + 1;
@@ -414,7 +414,7 @@ int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R, size_t N
     uint32_t* va = even ? bs.val_b : bs.val_a;
     uint32_t* kb = even ? bs.key_a : bs.key_b;
     uint32_t* vb = even ? bs.val_a : bs.val_b;
-    emit_cells_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, cells_x, g.order, g.offsets, g.rect, ka, va);
+    emit_cells_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, cells_x, g.order, g.offsets, g.rect_sorted, ka, va);
     count_launches(1);
     GSR_STAGE(s, debug, "emit_cells_kernel");
     prof_end(ST_EMIT_CELLS, s);

@@ -63,6 +63,8 @@ struct GeomState {
     uint32_t* val_a;          // [P]
     uint32_t* val_b;          // [P]
     uint32_t* order;          // alias of val_a: after the 4-pass depth sort, Gaussian ids front to back
+    uint32_t* cells_sorted;   // [P]  cells_touched in depth order (written by the last sort pass)
+    TileRect* rect_sorted;    // [P]  tile rectangles in depth order (written by the last sort pass)
     uint32_t* offsets;        // [P+1] exclusive scan of cells_touched in depth order
     uint32_t* radix_tmp;      // histogram / scan temporaries
     size_t    radix_tmp_count;
@@ -111,8 +113,15 @@ int launch_preprocess_fwd(const GsrForwardArgs& a, const GeomState& g, int ty0, 
 size_t radix_tmp_elems(size_t n);
 int radix_num_passes(int begin_bit, int end_bit);
 // input in (key_a,val_a); result in A if radix_num_passes() is even, else in B; both clobbered
+// optional side data delivered in sorted order by the LAST pass: out32[pos] = in32[val], out64[pos] = in64[val]
+struct RadixAux {
+    const uint32_t* in32;
+    uint32_t* out32;
+    const uint2* in64;
+    uint2* out64;
+};
 int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, size_t n,
-                     int begin_bit, int end_bit, uint32_t* tmp, cudaStream_t s, bool debug);
+                     int begin_bit, int end_bit, uint32_t* tmp, cudaStream_t s, bool debug, const RadixAux* aux = nullptr);
 // exclusive scan of gathered counts: out[i] = sum_{j<i} counts[perm[j]], out[n] = total
 int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, size_t n,
                   uint32_t* tmp, cudaStream_t s);

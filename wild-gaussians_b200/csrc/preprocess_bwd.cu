@@ -8,8 +8,8 @@
 // scale/rotation instead of being read back from the forward's scratch.  Every output row
 // is written here (zeros for Gaussians that were not rendered), so the host does not have
 // to zero-fill nine gradient tensors first (rasterize_points.cu:157-165).
-// The mixed fp32/fp64 steps of the reference's opacity-compensation gradient
-// (backward.cu:199-217) are kept as they are.
+// The reference's opacity-compensation gradient (backward.cu:199-217) is mixed fp32/fp64; it is evaluated in
+// fp32 here (gradients are compared at 1e-3; see the comment in the kernel).
 #include "common.cuh"
 #include "gaussian_math.cuh"
 #include <cstdlib>
@@ -205,17 +205,24 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
         Mat3 cov2D = e.cov;
         const float kernel_size = p.kernel_size;
 
-        const float det_0 = max(1e-6, (double)(cov2D.m[0][0] * cov2D.m[1][1] - cov2D.m[0][1] * cov2D.m[0][1]));
-        const float det_1 = max(1e-6, (double)((cov2D.m[0][0] + kernel_size) * (cov2D.m[1][1] + kernel_size) - cov2D.m[0][1] * cov2D.m[0][1]));
-        const float coef = sqrt(det_0 / (det_1 + 1e-6) + 1e-6);
+        // Opacity-compensation gradient (backward.cu:199-217).  The reference evaluates this block in double
+        // because of its double literals; only gradients (compared at 1e-3) depend on it, so it is evaluated in
+        // fp32 here -- about 350 instructions of fp64 division / square root per Gaussian less.  The two clamps
+        // and the det <= 1e-6 tests below select exactly the same branch as the double comparisons: no float lies
+        // strictly between (float)1e-6 and 1e-6.
+        const float det_0 = fmaxf(1e-6f, cov2D.m[0][0] * cov2D.m[1][1] - cov2D.m[0][1] * cov2D.m[0][1]);
+        const float det_1 = fmaxf(1e-6f, (cov2D.m[0][0] + kernel_size) * (cov2D.m[1][1] + kernel_size) - cov2D.m[0][1] * cov2D.m[0][1]);
+        const float inv_det1e = 1.0f / (det_1 + 1e-6f);
+        const float coef = sqrtf(det_0 * inv_det1e + 1e-6f);
 
-        const float opacity = combined_opacity / (coef + 1e-6);
+        const float inv_coefe = 1.0f / (coef + 1e-6f);
+        const float opacity = combined_opacity * inv_coefe;
         const float dL_dcoef = dL_dopacity * opacity;
-        const float dL_dsqrtcoef = dL_dcoef * 0.5 * 1. / (coef + 1e-6);
-        const float dL_ddet0 = dL_dsqrtcoef / (det_1 + 1e-6);
-        const float dL_ddet1 = dL_dsqrtcoef * det_0 * (-1.f / (det_1 * det_1 + 1e-6));
+        const float dL_dsqrtcoef = dL_dcoef * 0.5f * inv_coefe;
+        const float dL_ddet0 = dL_dsqrtcoef * inv_det1e;
+        const float dL_ddet1 = dL_dsqrtcoef * det_0 * (-1.f / (det_1 * det_1 + 1e-6f));
         const float dcoef_da = dL_ddet0 * cov2D.m[1][1] + dL_ddet1 * (cov2D.m[1][1] + kernel_size);
-        const float dcoef_db = dL_ddet0 * (-2. * cov2D.m[0][1]) + dL_ddet1 * (-2. * cov2D.m[0][1]);
+        const float dcoef_db = dL_ddet0 * (-2.f * cov2D.m[0][1]) + dL_ddet1 * (-2.f * cov2D.m[0][1]);
         const float dcoef_dc = dL_ddet0 * cov2D.m[0][0] + dL_ddet1 * (cov2D.m[0][0] + kernel_size);
 
         const float a = cov2D.m[0][0] += kernel_size;
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
             dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
             dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
 
-            if (det_0 <= 1e-6 || det_1 <= 1e-6) {
+            if (det_0 <= 1e-6f || det_1 <= 1e-6f) {
                 dL_dopacity = 0;
             } else {
                 dL_da += dcoef_da;
@@ -401,7 +408,7 @@ int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, const Bw
     static int occ = -1;
     if (occ < 0) {
         const char* e = getenv("GSR_PREBWD_OCC");    // tuning aid: resident CTAs per SM the register allocation targets
-        occ = e ? atoi(e) : 3;
+        occ = e ? atoi(e) : 4;
     }
     if (occ >= 4) preprocess_bwd_kernel<4><<<(a.P + 255) / 256, 256, 0, s>>>(p);
     else if (occ == 3) preprocess_bwd_kernel<3><<<(a.P + 255) / 256, 256, 0, s>>>(p);

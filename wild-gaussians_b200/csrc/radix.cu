@@ -23,7 +23,7 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;                       // items per thread
+constexpr int RS_ITEMS = 8;                        // items per thread (16 needs 99 registers: 2 CTAs/SM, latency-bound)
 constexpr int RS_CHUNK = RS_THREADS * RS_ITEMS;    // items per CTA
 constexpr int RS_WARP_ITEMS = 32 * RS_ITEMS;       // items per warp (contiguous in the input)
 
@@ -100,13 +100,14 @@ __global__ void __launch_bounds__(1024) radix_rowscan_kernel(uint32_t* __restric
     if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
 }
 
-template <bool WRITE_KEYS>
+template <bool WRITE_KEYS, bool AUX>
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                    const uint32_t* __restrict__ vals_in,
                                                                    uint32_t* __restrict__ keys_out,
                                                                    uint32_t* __restrict__ vals_out, size_t n, int shift,
                                                                    uint32_t mask, const uint32_t* __restrict__ hist,
-                                                                   const uint32_t* __restrict__ total, uint32_t ctas) {
+                                                                   const uint32_t* __restrict__ total, uint32_t ctas,
+                                                                   const RadixAux aux) {
     __shared__ uint32_t s_cnt[RS_WARPS][RADIX];   // per-warp digit counters, later global bases
     __shared__ uint32_t s_digit_base[RADIX];
     __shared__ uint32_t s_key[RS_CHUNK];
@@ -211,7 +212,14 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
         const uint32_t k = s_key[i];
         const uint32_t pos = i + s_digit_base[(k >> shift) & mask];
         if (WRITE_KEYS) keys_out[pos] = k;
-        vals_out[pos] = s_val[i];
+        const uint32_t v = s_val[i];
+        vals_out[pos] = v;
+        if (AUX) {
+            // final pass: also deliver the per-item side data in sorted order (one gather here instead of one in
+            // every later kernel that walks the sorted sequence)
+            aux.out32[pos] = aux.in32[v];
+            aux.out64[pos] = aux.in64[v];
+        }
     }
 }
 
@@ -229,7 +237,7 @@ int radix_num_passes(int begin_bit, int end_bit) {
 }
 
 int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, size_t n, int begin_bit,
-                     int end_bit, uint32_t* tmp, cudaStream_t s, bool debug) {
+                     int end_bit, uint32_t* tmp, cudaStream_t s, bool debug, const RadixAux* aux) {
     // Stable sort on key bits [begin_bit, end_bit).  The input is (key_a, val_a); passes
     // ping-pong A -> B -> A ..., clobbering both.  With an even number of passes
     // (radix_num_passes) the result is in A, with an odd number in B; callers place their
@@ -254,7 +262,10 @@ int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t
         radix_rowscan_kernel<<<RADIX, 1024, 0, s>>>(hist, ctas, total);
         count_launches(1);
         GSR_STAGE(s, debug, "radix_rowscan_kernel");
-        radix_scatter_kernel<true><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, total, ctas);
+        if (aux && pass == passes - 1)
+            radix_scatter_kernel<true, true><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, total, ctas, *aux);
+        else
+            radix_scatter_kernel<true, false><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, total, ctas, RadixAux{});
         count_launches(1);
         GSR_STAGE(s, debug, "radix_scatter_kernel");
     }

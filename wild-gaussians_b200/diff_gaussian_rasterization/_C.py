@@ -113,6 +113,7 @@ def get_tile_row_shard():
 # the same version counter (no in-place modification since), on the same stream, with the same scalar settings.
 # The entry keeps those tensors alive, so their addresses cannot be recycled for other data.  Modifying a tensor
 # behind autograd's back (``x.data.add_(...)``) does not bump the version: set GSR_GEOM_CACHE=0 for such code.
+_size_hint: dict = {}      # (P, W, H, shard) -> bytes of the binning / scratch buffers of the previous call
 _GEOM_CACHE_ON = os.environ.get("GSR_GEOM_CACHE", "1") != "0"
 _geom_cache: dict = {}
 
@@ -184,12 +185,16 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     dev = means3D.device
     P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
     with torch.cuda.device(dev):
-        out_color = torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
-        radii = torch.zeros((P,), dtype=torch.int32, device=dev)
         byte = dict(dtype=torch.uint8, device=dev)
         if P == 0:
             e = torch.empty((0,), **byte)
-            return 0, out_color, radii, e, e.clone(), e.clone()
+            return (0, torch.zeros((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev),
+                    torch.zeros((P,), dtype=torch.int32, device=dev), e, e.clone(), e.clone())
+        # every pixel of the rendered rows and every radii entry is written by the kernels: the reference's
+        # zero-fills (rasterize_points.cu:67-68) are only needed for the rows a tile-row shard leaves out
+        alloc_img = torch.empty if _shard == (0, 0) else torch.zeros
+        out_color = alloc_img((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
         M = int(sh.size(1)) if sh.numel() != 0 else 0
 
         keep = [_f32c(t, dev) for t in (background, means3D, colors, opacity, scales, rotations, cov3D_precomp,
@@ -233,13 +238,26 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 
         geom = torch.empty((gb.value,), **byte)
         img = torch.empty((ib.value,), **byte)
+        # The instance counts are known only after a device->host read-back inside gsr_forward_geometry.  To keep
+        # the GPU idle gap behind that synchronisation short, the two count-sized buffers are allocated beforehand
+        # from the sizes of the previous call with the same shape (training re-renders nearly the same scene) and
+        # re-allocated only if they turn out too small.
+        hint_key = (P, W, H, _shard)
+        hint = _size_hint.get(hint_key)
+        binning = scratch = None
+        if hint is not None:
+            binning = torch.empty((hint[0],), **byte)
+            scratch = torch.empty((hint[1],), **byte)
         R, N1 = c_int(0), c_int(0)
         _check(_lib.gsr_forward_geometry(byref(a), geom.data_ptr(), img.data_ptr(), stream, byref(R), byref(N1)),
                "gsr_forward_geometry")
         bb, sb = c_size_t(0), c_size_t(0)
         _check(_lib.gsr_binning_sizes(P, W, H, R.value, N1.value, byref(bb), byref(sb)), "gsr_binning_sizes")
-        binning = torch.empty((bb.value,), **byte)
-        scratch = torch.empty((sb.value,), **byte)
+        if binning is None or binning.numel() < bb.value:
+            binning = torch.empty((bb.value + bb.value // 16,), **byte)
+        if scratch is None or scratch.numel() < sb.value:
+            scratch = torch.empty((sb.value + sb.value // 16,), **byte)
+        _size_hint[hint_key] = (binning.numel(), scratch.numel())
         _check(_lib.gsr_forward_render(byref(a), geom.data_ptr(), img.data_ptr(), binning.data_ptr(),
                                        scratch.data_ptr(), R.value, N1.value, stream), "gsr_forward_render")
         # `scratch` goes back to torch's stream-ordered caching allocator here: any later
