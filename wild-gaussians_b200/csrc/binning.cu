@@ -15,9 +15,9 @@
 //            cell id groups them by cell, depth order preserved inside each cell.
 //   level 2  every cell's list is cut into units of 256 coarse items, one warp per unit.  A counting
 //            kernel histograms each unit over the cell's 64 tiles; a row scan turns the counts into the
-//            exact output position of every (unit, tile); the scatter kernel then walks each unit in
-//            order, 32 items at a time, and for every tile of the cell uses one ballot to rank the lanes
-//            covering it -- consecutive covering lanes write consecutive 4-byte slots of that tile's list.
+//            exact output position (and run length) of every (unit, tile); the scatter kernel then walks each unit
+//            in order: lane l owns the cell's tiles l and l + 32 and appends the ids of the items covering them to
+//            its slices of a shared-memory staging buffer, which is finally copied to the tile lists run by run.
 //
 // The order inside a tile is the order of the coarse items in the cell = depth order, ties by Gaussian
 // index (the depth sort is stable) -- exactly the reference's (tile | depth) stable sort (SURVEY.md note

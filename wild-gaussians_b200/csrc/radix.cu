@@ -10,11 +10,14 @@
 // id only (2 passes over R pairs) -- see binning.cu.
 //
 // One pass = three launches, no spin-waiting between CTAs (so nothing can dead-lock):
-//   radix_hist_kernel    per-CTA digit histogram of a CHUNK of the input   -> hist[digit][cta]
+//   radix_hist_kernel    per-CTA digit histogram of a CHUNK of the input (plain shared atomics) -> hist[digit][cta]
 //   radix_rowscan_kernel one CTA per digit: exclusive scan along the row    -> hist (in place), total[digit]
-//   radix_scatter_kernel re-reads the chunk, ranks every item among equal digits in
-//                        (warp, round, lane) = input order with match.any, and scatters
-// All traffic is coalesced on the read side; writes are digit-run coalesced.
+//   radix_scatter_kernel re-reads the chunk, ranks every item among equal digits in (warp, round, lane) = input
+//                        order -- the lanes holding the same digit are found with 8 ballots, one per digit bit;
+//                        __match_any_sync was measured 2-4x slower here because its cost grows with the number of
+//                        distinct digits in the warp -- then sorts the chunk in shared memory and writes it out so
+//                        that consecutive threads write consecutive addresses inside every digit run.
+// The last pass of a sort can also deliver side data in sorted order (RadixAux).
 #include "common.cuh"
 
 namespace gsr {
