@@ -310,8 +310,9 @@ def main():
                                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
             line["clocks"] = sampler.stop()
             line["gpu_launches"] = None
-            line["cpu_baseline"] = {"value": None, "kind": "reference", "cores": 0,
-                                    "sample": "n/a: this arm ran the reference's CUDA implementation on the GPU"}
+            line["cpu_baseline"] = {"value": line["value"], "unit": line["unit"], "kind": "reference", "cores": 0,
+                                    "sample": "the line's own value: the reference has no CPU implementation of this path, this "
+                                              "arm ran its unmodified CUDA implementation (oracle/_ref/libdgr_ref.so) on the GPU"}
         else:
             cb = cpu_baseline(a.config, kw)
             line.update(value=cb["value"], ms_per_step=None, cpu_baseline=cb,
