@@ -71,48 +71,60 @@ __global__ void __launch_bounds__(256) cell_bounds_kernel(const uint32_t* __rest
     if (i == n1 - 1) cell_range[c].y = n1;
 }
 
-// One CTA: units per cell (ceil(len / UNIT)) and their exclusive scan unit_base[0..NC];
-// unit_base[NC] = number of units.
-__global__ void __launch_bounds__(1024) build_units_kernel(const uint2* __restrict__ cell_range, uint32_t num_cells,
-                                                           uint32_t* __restrict__ unit_base) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
+// exclusive scan over the CTA's 1024 threads of two values at once; carries live in shared memory across calls
+__device__ __forceinline__ void block_scan2_1024(uint32_t& a, uint32_t& b, uint32_t* s_warp_a, uint32_t* s_warp_b,
+                                                 uint32_t* s_carry, uint32_t& excl_a, uint32_t& excl_b) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    uint32_t xa = a, xb = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t ya = __shfl_up_sync(0xFFFFFFFFu, xa, o), yb = __shfl_up_sync(0xFFFFFFFFu, xb, o);
+        if (lane >= o) { xa += ya; xb += yb; }
+    }
+    if (lane == 31) { s_warp_a[warp] = xa; s_warp_b[warp] = xb; }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wa = s_warp_a[lane], wb = s_warp_b[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ya = __shfl_up_sync(0xFFFFFFFFu, wa, o), yb = __shfl_up_sync(0xFFFFFFFFu, wb, o);
+            if (lane >= o) { wa += ya; wb += yb; }
+        }
+        s_warp_a[lane] = wa; s_warp_b[lane] = wb;
+    }
+    __syncthreads();
+    excl_a = s_carry[0] + (warp == 0 ? 0u : s_warp_a[warp - 1]) + xa - a;
+    excl_b = s_carry[1] + (warp == 0 ? 0u : s_warp_b[warp - 1]) + xb - b;
+    __syncthreads();
+    if (threadIdx.x == 1023) { s_carry[0] += s_warp_a[31]; s_carry[1] += s_warp_b[31]; }
+    __syncthreads();
+}
+
+// One CTA: units per cell (ceil(len / UNIT)) and their exclusive scan unit_base[0..NC]; unit_base[NC] = number of
+// units.  With cell_count != NULL (the digit totals of a single-pass cell sort = items per cell) the cell ranges
+// are derived here too, instead of by cell_bounds_kernel.
+__global__ void __launch_bounds__(1024) build_units_kernel(uint2* __restrict__ cell_range, uint32_t num_cells,
+                                                           uint32_t* __restrict__ unit_base,
+                                                           const uint32_t* __restrict__ cell_count) {
+    __shared__ uint32_t s_wa[32], s_wb[32], s_carry[2];
+    if (threadIdx.x < 2) s_carry[threadIdx.x] = 0;
     __syncthreads();
     for (uint32_t base = 0; base < num_cells; base += 1024) {
         const uint32_t i = base + threadIdx.x;
-        uint32_t v = 0;
+        uint32_t len = 0;
         if (i < num_cells) {
-            const uint2 cr = cell_range[i];
-            v = (cr.y - cr.x + UNIT - 1) / UNIT;
+            if (cell_count) len = cell_count[i];
+            else { const uint2 cr = cell_range[i]; len = cr.y - cr.x; }
         }
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
+        uint32_t units = (len + UNIT - 1) / UNIT, ex_units, ex_len;
+        block_scan2_1024(units, len, s_wa, s_wb, s_carry, ex_units, ex_len);
+        if (i < num_cells) {
+            unit_base[i] = ex_units;
+            // empty cells keep (0, 0) like cell_bounds_kernel leaves them
+            if (cell_count) cell_range[i] = len ? make_uint2(ex_len, ex_len + len) : make_uint2(0u, 0u);
         }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
-                if (lane >= o) w += y;
-            }
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        const uint32_t warp_excl = warp == 0 ? 0u : s_warp[warp - 1];
-        const uint32_t carry = s_carry;
-        if (i < num_cells) unit_base[i] = carry + warp_excl + x - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
-        __syncthreads();
     }
-    if (threadIdx.x == 0) unit_base[num_cells] = s_carry;
+    if (threadIdx.x == 0) unit_base[num_cells] = s_carry[0];
 }
 
 // unit u belongs to the cell c with unit_base[c] <= u < unit_base[c+1]
@@ -174,28 +186,32 @@ __device__ __forceinline__ uint32_t prefix_at(const uint32_t* __restrict__ Pm, c
     return u >= cap ? row_total[t] : Pm[(size_t)t * cap + u];
 }
 
-__global__ void __launch_bounds__(256) tile_counts_kernel(const uint32_t* __restrict__ Pm, const uint32_t* __restrict__ row_total,
-                                                          const uint32_t* __restrict__ unit_base, uint32_t num_cells,
-                                                          uint32_t cap, int cells_x, int grid_x, int grid_y,
-                                                          uint32_t* __restrict__ tile_count) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // (cell, local tile)
-    if (i >= num_cells * CELL_TILES) return;
-    const uint32_t c = i / CELL_TILES, t = i % CELL_TILES;
-    const int tx = (int)(c % cells_x) * CELL + (int)(t % CELL), ty = (int)(c / cells_x) * CELL + (int)(t / CELL);
-    if (tx >= grid_x || ty >= grid_y) return;
-    const uint32_t a = prefix_at(Pm, row_total, cap, t, unit_base[c]);
-    const uint32_t b = prefix_at(Pm, row_total, cap, t, unit_base[c + 1]);
-    tile_count[ty * grid_x + tx] = b - a;
-}
-
-// ranges[t] = [start, start + count); empty tiles are (0, 0) like the reference (rasterizer_impl.cu:313)
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ tile_start,
-                                                          const uint32_t* __restrict__ tile_count, int num_tiles,
-                                                          uint2* __restrict__ ranges) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= num_tiles) return;
-    const uint32_t c = tile_count[t], s = tile_start[t];
-    ranges[t] = c ? make_uint2(s, s + c) : make_uint2(0u, 0u);
+// One CTA: per-tile instance counts (differences of the row-scanned count matrix at the cell's unit boundaries),
+// their exclusive scan in global tile order and the tile ranges -- replaces a memset and five small launches.
+// ranges[t] = [start, start + count); empty tiles are (0, 0) like the reference (rasterizer_impl.cu:313).
+__global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* __restrict__ Pm, const uint32_t* __restrict__ row_total,
+                                                            const uint32_t* __restrict__ unit_base, uint32_t cap, int cells_x,
+                                                            int grid_x, int num_tiles, uint32_t* __restrict__ tile_start,
+                                                            uint2* __restrict__ ranges) {
+    __shared__ uint32_t s_wa[32], s_wb[32], s_carry[2];
+    if (threadIdx.x < 2) s_carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int base = 0; base < num_tiles; base += 1024) {
+        const int t = base + (int)threadIdx.x;
+        uint32_t cnt = 0, dummy = 0, start, ex_dummy;
+        if (t < num_tiles) {
+            const int tx = t % grid_x, ty = t / grid_x;
+            const uint32_t c = (uint32_t)((ty / CELL) * cells_x + tx / CELL), lt = (uint32_t)((ty % CELL) * CELL + tx % CELL);
+            cnt = prefix_at(Pm, row_total, cap, lt, unit_base[c + 1]) - prefix_at(Pm, row_total, cap, lt, unit_base[c]);
+        }
+        const uint32_t mine = cnt;
+        block_scan2_1024(cnt, dummy, s_wa, s_wb, s_carry, start, ex_dummy);
+        if (t < num_tiles) {
+            tile_start[t] = start;
+            ranges[t] = mine ? make_uint2(start, start + mine) : make_uint2(0u, 0u);
+        }
+    }
+    if (threadIdx.x == 0) tile_start[num_tiles] = s_carry[0];
 }
 
 // ---- level 2c: scatter ------------------------------------------------------------------------------
@@ -428,11 +444,17 @@ int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R, size_t N
 
     // units + per-unit tile counts
     const uint32_t cap = (uint32_t)bs.units_cap;
-    GSR_CUDA(cudaMemsetAsync(bs.cell_range, 0, (size_t)num_cells * sizeof(uint2), s));
-    cell_bounds_kernel<<<(unsigned)((N1 + 255) / 256), 256, 0, s>>>(keys, (uint32_t)N1, bs.cell_range);
-    count_launches(1);
-    build_units_kernel<<<1, 1024, 0, s>>>(bs.cell_range, num_cells, bs.unit_base);
-    count_launches(1);
+    if (radix_num_passes(0, cell_bits) == 1) {
+        // one pass sorted by the whole cell id: its digit totals ARE the items per cell
+        build_units_kernel<<<1, 1024, 0, s>>>(bs.cell_range, num_cells, bs.unit_base, radix_pass_totals(bs.radix_tmp, N1));
+        count_launches(1);
+    } else {
+        GSR_CUDA(cudaMemsetAsync(bs.cell_range, 0, (size_t)num_cells * sizeof(uint2), s));
+        cell_bounds_kernel<<<(unsigned)((N1 + 255) / 256), 256, 0, s>>>(keys, (uint32_t)N1, bs.cell_range);
+        count_launches(1);
+        build_units_kernel<<<1, 1024, 0, s>>>(bs.cell_range, num_cells, bs.unit_base, nullptr);
+        count_launches(1);
+    }
     GSR_STAGE(s, debug, "build_units_kernel");
     cell_count_kernel<<<(cap + 7) / 8, 256, 0, s>>>(keys, bs.unit_base, bs.cell_range, num_cells, cap, bs.M);
     count_launches(1);
@@ -443,15 +465,9 @@ int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R, size_t N
     // exact output positions
     rc = row_scan_u32(bs.M, CELL_TILES, cap, bs.row_total, s);
     if (rc) return rc;
-    GSR_CUDA(cudaMemsetAsync(bs.tile_count, 0, ((size_t)num_tiles + 1) * sizeof(uint32_t), s));
-    tile_counts_kernel<<<(num_cells * CELL_TILES + 255) / 256, 256, 0, s>>>(bs.M, bs.row_total, bs.unit_base, num_cells, cap,
-                                                                         cells_x, gx, gy, bs.tile_count);
+    tile_offsets_kernel<<<1, 1024, 0, s>>>(bs.M, bs.row_total, bs.unit_base, cap, cells_x, gx, num_tiles, bs.tile_start, ranges);
     count_launches(1);
-    rc = scan_gathered(bs.tile_count, nullptr, bs.tile_start, (size_t)num_tiles, bs.scan_tmp, s);
-    if (rc) return rc;
-    tile_ranges_kernel<<<(num_tiles + 255) / 256, 256, 0, s>>>(bs.tile_start, bs.tile_count, num_tiles, ranges);
-    count_launches(1);
-    GSR_STAGE(s, debug, "tile_ranges_kernel");
+    GSR_STAGE(s, debug, "tile_offsets_kernel");
     prof_end(ST_TILE_OFFSETS, s);
     prof_begin(ST_TILE_SCATTER, s);
 

@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
     }
 }
 
+const uint32_t* radix_pass_totals(const uint32_t* tmp, size_t n) { return tmp + (size_t)RADIX * radix_ctas(n); }
+
 int row_scan_u32(uint32_t* m, int rows, size_t cols, uint32_t* total, cudaStream_t s) {
     if (rows <= 0 || cols == 0) return 0;
     radix_rowscan_kernel<<<rows, 1024, 0, s>>>(m, (uint32_t)cols, total);
