@@ -37,7 +37,7 @@ struct RenderFwdParams {
     float* out_color;
 };
 
-template <int PPT, bool FLAT>
+template <int PPT>
 __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_fwd_kernel(const __grid_constant__ RenderFwdParams p) {
     using PM = PixelMap<PPT>;
     constexpr int THREADS = PM::THREADS;
@@ -142,29 +142,6 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_fwd_kernel(cons
                         mm &= mm - 1;
                         const float4 geo = s_geo[buf][j];
                         const float4 con_o = s_con[buf][j];
-                        if (FLAT) {
-                            // branch-light form: every lane evaluates the pair, the state update is predicated.
-                            // Same expressions, same tests, same results as the branchy form below.
-#pragma unroll
-                            for (int k = 0; k < PPT; ++k) {
-                                const float2 d = {geo.x - pixf[k].x, geo.y - pixf[k].y};
-                                const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-                                const float alpha = min(0.99f, con_o.w * expf(power));
-                                const float test_T = T[k] * (1 - alpha);
-                                const bool blend = (live & (1u << k)) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                                const bool stop = blend && test_T < 0.0001f;
-                                if (stop) live &= ~(1u << k);
-                                if (blend && !stop) {
-                                    const float4 col = s_col[buf][j];
-                                    C0[k] += col.x * alpha * T[k];
-                                    C1[k] += col.y * alpha * T[k];
-                                    C2[k] += col.z * alpha * T[k];
-                                    T[k] = test_T;
-                                    last_contributor[k] = round_base + (uint32_t)j + 1u;
-                                }
-                            }
-                            continue;
-                        }
 #pragma unroll
                         for (int k = 0; k < PPT; ++k) {
                             if (!(live & (1u << k))) continue;
@@ -414,17 +391,10 @@ int launch_render_fwd(const GsrForwardArgs& a, const GeomState& g, const BinStat
         count_launches(1);
         return 0;
     }
-    static int flat = -1;
-    if (flat < 0) {
-        const char* e = getenv("GSR_FWD_FLAT");      // tuning aid: 1 = predicated (branch-light) blend loop
-        flat = e ? atoi(e) : 0;
-    }
-    switch (fwd_ppt() + (flat ? 8 : 0)) {
-        case 1: render_fwd_kernel<1, false><<<grid, PixelMap<1>::THREADS, 0, s>>>(p); break;
-        case 4: render_fwd_kernel<4, false><<<grid, PixelMap<4>::THREADS, 0, s>>>(p); break;
-        case 9: render_fwd_kernel<1, true><<<grid, PixelMap<1>::THREADS, 0, s>>>(p); break;
-        case 10: render_fwd_kernel<2, true><<<grid, PixelMap<2>::THREADS, 0, s>>>(p); break;
-        default: render_fwd_kernel<2, false><<<grid, PixelMap<2>::THREADS, 0, s>>>(p); break;
+    switch (fwd_ppt()) {
+        case 1: render_fwd_kernel<1><<<grid, PixelMap<1>::THREADS, 0, s>>>(p); break;
+        case 4: render_fwd_kernel<4><<<grid, PixelMap<4>::THREADS, 0, s>>>(p); break;
+        default: render_fwd_kernel<2><<<grid, PixelMap<2>::THREADS, 0, s>>>(p); break;
     }
     count_launches(1);
     return 0;
