@@ -18,6 +18,7 @@ namespace gsr {
 
 struct PreBwdParams {
     int P, D, M;
+    int sh_vec;             // SH rows are 16-byte aligned multiples of 16 bytes
     float focal_x, focal_y, tan_fovx, tan_fovy, kernel_size, scale_modifier;
     const float* means3D;
     const int* radii;
@@ -53,9 +54,11 @@ __device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
     return r;
 }
 
-// SH colour backward (backward.cu:20-139): writes dL_dsh rows, returns the mean gradient
-// caused by the view direction.
-__device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const float* __restrict__ sh_base, float3 mean,
+// SH colour backward (backward.cu:20-139): writes the dL_dsh row, returns the mean gradient caused by the view
+// direction.  `vec`: rows are aligned multiples of 16 bytes -- the coefficients are read and the gradient row is
+// written with 128-bit accesses (a scalar access pattern makes every instruction of a warp touch 32 sectors, one per
+// Gaussian, and the kernel becomes bound by L1/L2 sector traffic: measured 8x slower per Gaussian).
+__device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const float* __restrict__ sh_base, bool vec, float3 mean,
                                               const float* __restrict__ campos, unsigned clamp_bits, V3 dL_dRGB,
                                               float* __restrict__ dL_dsh_base) {
     V3 pos = {mean.x, mean.y, mean.z};
@@ -68,21 +71,38 @@ __device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const flo
     dL_dRGB.y *= (clamp_bits & 2u) ? 0 : 1;
     dL_dRGB.z *= (clamp_bits & 4u) ? 0 : 1;
 
+    const int used = (deg + 1) * (deg + 1);
+    float shl[48];
+    if (vec) {
+        const float4* p4 = reinterpret_cast<const float4*>(sh_base);
+        const int n4 = (3 * used + 3) >> 2;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            if (i < n4) {
+                const float4 v = __ldg(p4 + i);
+                shl[4 * i + 0] = v.x; shl[4 * i + 1] = v.y; shl[4 * i + 2] = v.z; shl[4 * i + 3] = v.w;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 48; ++i)
+            if (i < 3 * used) shl[i] = sh_base[i];
+    }
+
     V3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
     const float x = dir.x, y = dir.y, z = dir.z;
 
-    auto sh = [&](int k) { return ldv3(sh_base + 3 * k); };
-    auto put = [&](int k, float w) {
-        dL_dsh_base[3 * k + 0] = w * dL_dRGB.x;
-        dL_dsh_base[3 * k + 1] = w * dL_dRGB.y;
-        dL_dsh_base[3 * k + 2] = w * dL_dRGB.z;
-    };
+    auto sh = [&](int k) { return V3{shl[3 * k], shl[3 * k + 1], shl[3 * k + 2]}; };
+    // basis weight of every coefficient (0 above the active degree: those receive no gradient)
+    float w[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = 0.f;
 
-    put(0, GSR_SH_C0);
+    w[0] = GSR_SH_C0;
     if (deg > 0) {
-        put(1, -GSR_SH_C1 * y);
-        put(2, GSR_SH_C1 * z);
-        put(3, -GSR_SH_C1 * x);
+        w[1] = -GSR_SH_C1 * y;
+        w[2] = GSR_SH_C1 * z;
+        w[3] = -GSR_SH_C1 * x;
 
         dRGBdx = -GSR_SH_C1 * sh(3);
         dRGBdy = -GSR_SH_C1 * sh(1);
@@ -91,24 +111,24 @@ __device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const flo
         if (deg > 1) {
             const float xx = x * x, yy = y * y, zz = z * z;
             const float xy = x * y, yz = y * z, xz = x * z;
-            put(4, GSR_SH_C2_0 * xy);
-            put(5, GSR_SH_C2_1 * yz);
-            put(6, GSR_SH_C2_2 * (2.f * zz - xx - yy));
-            put(7, GSR_SH_C2_3 * xz);
-            put(8, GSR_SH_C2_4 * (xx - yy));
+            w[4] = GSR_SH_C2_0 * xy;
+            w[5] = GSR_SH_C2_1 * yz;
+            w[6] = GSR_SH_C2_2 * (2.f * zz - xx - yy);
+            w[7] = GSR_SH_C2_3 * xz;
+            w[8] = GSR_SH_C2_4 * (xx - yy);
 
             dRGBdx += GSR_SH_C2_0 * y * sh(4) + GSR_SH_C2_2 * 2.f * -x * sh(6) + GSR_SH_C2_3 * z * sh(7) + GSR_SH_C2_4 * 2.f * x * sh(8);
             dRGBdy += GSR_SH_C2_0 * x * sh(4) + GSR_SH_C2_1 * z * sh(5) + GSR_SH_C2_2 * 2.f * -y * sh(6) + GSR_SH_C2_4 * 2.f * -y * sh(8);
             dRGBdz += GSR_SH_C2_1 * y * sh(5) + GSR_SH_C2_2 * 2.f * 2.f * z * sh(6) + GSR_SH_C2_3 * x * sh(7);
 
             if (deg > 2) {
-                put(9, GSR_SH_C3_0 * y * (3.f * xx - yy));
-                put(10, GSR_SH_C3_1 * xy * z);
-                put(11, GSR_SH_C3_2 * y * (4.f * zz - xx - yy));
-                put(12, GSR_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy));
-                put(13, GSR_SH_C3_4 * x * (4.f * zz - xx - yy));
-                put(14, GSR_SH_C3_5 * z * (xx - yy));
-                put(15, GSR_SH_C3_6 * x * (xx - 3.f * yy));
+                w[9] = GSR_SH_C3_0 * y * (3.f * xx - yy);
+                w[10] = GSR_SH_C3_1 * xy * z;
+                w[11] = GSR_SH_C3_2 * y * (4.f * zz - xx - yy);
+                w[12] = GSR_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                w[13] = GSR_SH_C3_4 * x * (4.f * zz - xx - yy);
+                w[14] = GSR_SH_C3_5 * z * (xx - yy);
+                w[15] = GSR_SH_C3_6 * x * (xx - 3.f * yy);
 
                 dRGBdx += (GSR_SH_C3_0 * sh(9) * 3.f * 2.f * xy +
                            GSR_SH_C3_1 * sh(10) * yz +
@@ -132,19 +152,40 @@ __device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const flo
             }
         }
     }
-    // coefficients above the active degree receive no gradient
-    const int used = (deg + 1) * (deg + 1);
-    for (int k = used; k < max_coeffs; ++k) {
-        dL_dsh_base[3 * k + 0] = 0.f;
-        dL_dsh_base[3 * k + 1] = 0.f;
-        dL_dsh_base[3 * k + 2] = 0.f;
+    // dL_dsh[k][c] = w[k] * dL_dRGB[c]; coefficients above the active degree get 0 (w[k] = 0)
+    if (vec) {
+        float4* o4 = reinterpret_cast<float4*>(dL_dsh_base);
+        const int groups = (max_coeffs * 3) >> 2;   // 4 coefficients (12 floats) = 3 float4 per group of four
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+            if (3 * g4 < groups) {
+                const float w0 = w[4 * g4], w1 = w[4 * g4 + 1], w2 = w[4 * g4 + 2], w3 = w[4 * g4 + 3];
+                o4[3 * g4 + 0] = make_float4(w0 * dL_dRGB.x, w0 * dL_dRGB.y, w0 * dL_dRGB.z, w1 * dL_dRGB.x);
+                o4[3 * g4 + 1] = make_float4(w1 * dL_dRGB.y, w1 * dL_dRGB.z, w2 * dL_dRGB.x, w2 * dL_dRGB.y);
+                o4[3 * g4 + 2] = make_float4(w2 * dL_dRGB.z, w3 * dL_dRGB.x, w3 * dL_dRGB.y, w3 * dL_dRGB.z);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k < max_coeffs) {
+                dL_dsh_base[3 * k + 0] = w[k] * dL_dRGB.x;
+                dL_dsh_base[3 * k + 1] = w[k] * dL_dRGB.y;
+                dL_dsh_base[3 * k + 2] = w[k] * dL_dRGB.z;
+            }
+        }
+        for (int k = 16; k < max_coeffs; ++k) {      // tensors holding more than degree-3 coefficients
+            dL_dsh_base[3 * k + 0] = 0.f;
+            dL_dsh_base[3 * k + 1] = 0.f;
+            dL_dsh_base[3 * k + 2] = 0.f;
+        }
     }
 
     const float3 dL_ddir = {dot3(dRGBdx, dL_dRGB), dot3(dRGBdy, dL_dRGB), dot3(dRGBdz, dL_dRGB)};
     return dnormvdv3(float3{dir_orig.x, dir_orig.y, dir_orig.z}, dL_ddir);
 }
 
-template <int MIN_CTAS>
+template <int MIN_CTAS, bool HAS_SH>
 __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __grid_constant__ PreBwdParams p) {
     __shared__ float s_view[16];
     __shared__ float s_proj[16];
@@ -310,8 +351,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
         o_mean3D[2] = dL_dmean_cov.z + dL_dmean.z;
 
         // ---- SH backward (backward.cu:20-139) ----
-        if (p.shs != nullptr) {
-            const float3 g = sh_backward(p.D, p.M, p.shs + (size_t)idx * p.M * 3, mean, p.campos, p.clamped[idx],
+        if (HAS_SH) {
+            const float3 g = sh_backward(p.D, p.M, p.shs + (size_t)idx * p.M * 3, p.sh_vec != 0, mean, p.campos, p.clamped[idx],
                                          V3{o_color[0], o_color[1], o_color[2]}, p.dL_dsh + (size_t)idx * p.M * 3);
             o_mean3D[0] += g.x;
             o_mean3D[1] += g.y;
@@ -379,9 +420,14 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
 #pragma unroll
         for (int k = 0; k < 6; ++k) p.dL_dcov3D[6 * i + k] = o_cov3D[k];
     }
-    if (p.dL_dsh && !sh_written) {
+    if (HAS_SH && !sh_written) {
         float* row = p.dL_dsh + i * p.M * 3;
-        for (int k = 0; k < p.M * 3; ++k) row[k] = 0.f;
+        if (p.sh_vec) {
+            float4* r4 = reinterpret_cast<float4*>(row);
+            for (int k = 0; k < (p.M * 3) >> 2; ++k) r4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int k = 0; k < p.M * 3; ++k) row[k] = 0.f;
+        }
     }
     if (p.dL_dscale) {
         p.dL_dscale[3 * i + 0] = o_scale[0];
@@ -410,9 +456,12 @@ int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, const Bw
         const char* e = getenv("GSR_PREBWD_OCC");    // tuning aid: resident CTAs per SM the register allocation targets
         occ = e ? atoi(e) : 4;
     }
-    if (occ >= 4) preprocess_bwd_kernel<4><<<(a.P + 255) / 256, 256, 0, s>>>(p);
-    else if (occ == 3) preprocess_bwd_kernel<3><<<(a.P + 255) / 256, 256, 0, s>>>(p);
-    else preprocess_bwd_kernel<2><<<(a.P + 255) / 256, 256, 0, s>>>(p);
+    p.sh_vec = a.shs != nullptr && (a.M == 4 || a.M == 16) &&
+               (reinterpret_cast<uintptr_t>(a.shs) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.dL_dsh) & 15u) == 0;
+    if (a.shs != nullptr) preprocess_bwd_kernel<2, true><<<(a.P + 255) / 256, 256, 0, s>>>(p);   // 48 + 16 extra live registers
+    else if (occ >= 4) preprocess_bwd_kernel<4, false><<<(a.P + 255) / 256, 256, 0, s>>>(p);
+    else if (occ == 3) preprocess_bwd_kernel<3, false><<<(a.P + 255) / 256, 256, 0, s>>>(p);
+    else preprocess_bwd_kernel<2, false><<<(a.P + 255) / 256, 256, 0, s>>>(p);
     count_launches(1);
     return 0;
 }

@@ -22,6 +22,7 @@ struct PreFwdParams {
     int ty0, ty1;                 // tile-row shard
     float focal_x, focal_y, tan_fovx, tan_fovy, kernel_size, scale_modifier;
     int prefiltered;
+    int sh_vec;                   // SH rows are 16-byte aligned multiples of 16 bytes: 128-bit loads
     const float* means3D;
     const float* shs;
     const float* colors_precomp;
@@ -55,8 +56,32 @@ __device__ __forceinline__ float ndc_to_pix(float v, int S) {
 // and the colours must have the reference's bits), so every product / sum is spelled out with
 // non-contractable intrinsics in exactly the order nvcc emits for the reference (read off its SASS and
 // pinned by tests/golden): each term is accumulated with one fma, res = fma(w_k, sh_k, res).
-__device__ __forceinline__ V3 sh_to_rgb(int deg, const float* __restrict__ sh, float3 p, const float* __restrict__ campos,
-                                        unsigned* clamp_bits) {
+// The coefficients of one Gaussian are (max_deg+1)^2 * 3 contiguous floats.  Reading them with scalar loads
+// makes every load instruction of a warp touch 32 different sectors (stride = one Gaussian); with 48 such loads the
+// kernel is bound by L1 sector look-ups (measured 6x slower per Gaussian than the precomputed-colour path).  When a
+// row is a whole number of 16-byte words and aligned, it is fetched with 128-bit loads instead (12 instead of 48).
+__device__ __forceinline__ void load_sh_row(float (&dst)[48], const float* __restrict__ sh, int n_floats, bool vec) {
+    if (vec) {
+        const float4* p4 = reinterpret_cast<const float4*>(sh);
+        const int n4 = (n_floats + 3) >> 2;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            if (i < n4) {
+                const float4 v = __ldg(p4 + i);
+                dst[4 * i + 0] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 48; ++i)
+            if (i < n_floats) dst[i] = sh[i];
+    }
+}
+
+__device__ __forceinline__ V3 sh_to_rgb(int deg, const float* __restrict__ sh_row, bool vec, float3 p,
+                                        const float* __restrict__ campos, unsigned* clamp_bits) {
+    float sh[48];
+    load_sh_row(sh, sh_row, 3 * (deg + 1) * (deg + 1), vec);
     const float dx = __fsub_rn(p.x, campos[0]), dy = __fsub_rn(p.y, campos[1]), dz = __fsub_rn(p.z, campos[2]);
     const float len = __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
     const float x = __fdiv_rn(dx, len), y = __fdiv_rn(dy, len), z = __fdiv_rn(dz, len);
@@ -104,6 +129,7 @@ __device__ __forceinline__ V3 sh_to_rgb(int deg, const float* __restrict__ sh, f
     return out;
 }
 
+template <bool HAS_SH>
 __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_constant__ PreFwdParams p) {
     // camera matrices: one coalesced read per block into shared memory
     __shared__ float s_view[16];
@@ -184,9 +210,9 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         if ((rx1 - rx0) * (ry1 - ry0) == 0) break;
 
         // colour from SH (the colors_precomp path reads colours only while compositing)
-        if (p.colors_precomp == nullptr) {
+        if (HAS_SH) {
             unsigned bits;
-            const V3 c = sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, p_orig, p.campos, &bits);
+            const V3 c = sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, p.sh_vec != 0, p_orig, p.campos, &bits);
             p.rgb[3 * idx + 0] = c.x;
             p.rgb[3 * idx + 1] = c.y;
             p.rgb[3 * idx + 2] = c.z;
@@ -254,6 +280,7 @@ int launch_preprocess_fwd(const GsrForwardArgs& a, const GeomState& g, int ty0, 
     p.tan_fovx = a.tan_fovx; p.tan_fovy = a.tan_fovy;
     p.kernel_size = a.kernel_size; p.scale_modifier = a.scale_modifier;
     p.prefiltered = a.prefiltered;
+    p.sh_vec = a.shs != nullptr && (a.M * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(a.shs) & 15u) == 0;
     p.means3D = a.means3D; p.shs = a.shs; p.colors_precomp = a.colors_precomp;
     p.opacities = a.opacities; p.scales = a.scales; p.rotations = a.rotations;
     p.cov3D_precomp = a.cov3D_precomp; p.campos = a.campos;
@@ -262,7 +289,8 @@ int launch_preprocess_fwd(const GsrForwardArgs& a, const GeomState& g, int ty0, 
     p.tiles_touched = g.tiles_touched; p.cells_touched = g.cells_touched; p.rect = g.rect;
     p.sort_key = g.key_a; p.sort_val = g.val_a; p.counters = g.counters;
     const int blocks = (a.P + 255) / 256;
-    preprocess_fwd_kernel<<<blocks, 256, 0, s>>>(p);
+    if (a.colors_precomp == nullptr) preprocess_fwd_kernel<true><<<blocks, 256, 0, s>>>(p);
+    else preprocess_fwd_kernel<false><<<blocks, 256, 0, s>>>(p);
     count_launches(1);
     return 0;
 }
