@@ -334,7 +334,7 @@ def test_prefiltered_violation_raises(C, dev):
 # ------------------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE.json's full sizes
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cfg", ["C2", "C3"])
+@pytest.mark.parametrize("cfg", ["C2", "C3", "C5"])
 def test_full_size_properties(C, dev, cfg):
     kw = dict(synthetic.CONFIGS[cfg]); kw["seed"] = 0
     scene = synthetic.make_scene(**kw)

@@ -298,12 +298,13 @@ __device__ __forceinline__ uint4 item_record(uint32_t key, uint32_t id) {
     return make_uint4(lo, hi, id, 0u);
 }
 
-// MODE 0: stage both tile halves; 1: only tiles 0-31; 2: only tiles 32-63; 3: direct global stores (no staging)
-template <int MODE>
+// One walk over the unit's coarse items: every lane appends the ids of the items covering "its" tiles (bit0 /
+// bit1 select them in the two coverage words; 0 = this lane's tile is not part of the walk) to its slices of the
+// staging buffer through the cursors a0 / a1.
+template <bool S0, bool S1>
 __device__ __forceinline__ void scatter_walk(const UnitInfo& ui, const uint32_t* __restrict__ keys,
-                                             const uint32_t* __restrict__ vals, uint4* s_item, int lane, uint32_t a0,
-                                             uint32_t a1, uint32_t* __restrict__ point_list) {
-    const uint32_t bit = 1u << lane;
+                                             const uint32_t* __restrict__ vals, uint4* s_item, int lane, uint32_t bit0,
+                                             uint32_t bit1, uint32_t a0, uint32_t a1) {
     uint32_t key = 0, id = 0;
     if ((uint32_t)lane < ui.count) { key = keys[ui.first + lane]; id = vals[ui.first + lane]; }
     for (uint32_t base = 0; base < ui.count; base += 32) {
@@ -317,12 +318,8 @@ __device__ __forceinline__ void scatter_walk(const UnitInfo& ui, const uint32_t*
 #pragma unroll 4
         for (int i = 0; i < nitems; ++i) {
             const uint4 it = s_item[i];
-            if (MODE == 0 || MODE == 1) sts_append(a0, it.z, it.x & bit);
-            if (MODE == 0 || MODE == 2) sts_append(a1, it.z, it.y & bit);
-            if (MODE == 3) {
-                if (it.x & bit) point_list[a0++] = it.z;
-                if (it.y & bit) point_list[a1++] = it.z;
-            }
+            if (S0) sts_append(a0, it.z, it.x & bit0);
+            if (S1) sts_append(a1, it.z, it.y & bit1);
         }
     }
     __syncwarp();
@@ -376,8 +373,8 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) cell_scatter_staged_kernel(
         pos[h] = p;
         len[h] = l;
     }
-    // staging slice of every tile: exclusive scan of the run lengths inside each half (tiles 0..31, 32..63)
-    uint32_t off[2], tot[2];
+    // exclusive prefix of the run lengths in tile order (0..63): the staging slice of every tile
+    uint32_t pre[2];
     {
         uint32_t x0 = len[0], x1 = len[1];
 #pragma unroll
@@ -385,28 +382,47 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) cell_scatter_staged_kernel(
             const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, x0, o), y1 = __shfl_up_sync(0xFFFFFFFFu, x1, o);
             if (lane >= o) { x0 += y0; x1 += y1; }
         }
-        tot[0] = __shfl_sync(0xFFFFFFFFu, x0, 31);
-        tot[1] = __shfl_sync(0xFFFFFFFFu, x1, 31);
-        off[0] = x0 - len[0];
-        off[1] = x1 - len[1];
+        const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
+        pre[0] = x0 - len[0];
+        pre[1] = tot0 + x1 - len[1];
     }
+    // The unit's output is staged in as few walks as possible: the cell's 8 tile rows are cut greedily into
+    // groups of consecutive rows whose runs fit the staging buffer together.  One row always fits (at most
+    // UNIT items x 8 tiles = SQ_ENTRIES entries), typical units need a single walk over all rows.
+    static_assert(UNIT * CELL <= SQ_ENTRIES, "one tile row of a unit must fit the staging buffer");
+    // pre_row(r) = entries in rows < r = prefix at tile 8 r  (r = 0..8)
+    auto pre_row = [&](int r) -> uint32_t {
+        if (r >= 8) return __shfl_sync(0xFFFFFFFFu, pre[1] + len[1], 31);
+        return r < 4 ? __shfl_sync(0xFFFFFFFFu, pre[0], 8 * r) : __shfl_sync(0xFFFFFFFFu, pre[1], 8 * (r - 4));
+    };
     const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(q);
-    // all branches below are warp-uniform
-    if (tot[0] + tot[1] <= (uint32_t)SQ_ENTRIES) {
-        off[1] += tot[0];
-        scatter_walk<0>(ui, keys, vals, s_item, lane, q_addr + 4u * off[0], q_addr + 4u * off[1], point_list);
-        scatter_copy_out(q, len[0], off[0], pos[0], lane, point_list);
-        scatter_copy_out(q, len[1], off[1], pos[1], lane, point_list);
-    } else if (max(tot[0], tot[1]) <= (uint32_t)SQ_ENTRIES) {
-        // two walks over the unit's items, one tile half each
-        scatter_walk<1>(ui, keys, vals, s_item, lane, q_addr + 4u * off[0], 0u, point_list);
-        scatter_copy_out(q, len[0], off[0], pos[0], lane, point_list);
-        __syncwarp();
-        scatter_walk<2>(ui, keys, vals, s_item, lane, 0u, q_addr + 4u * off[1], point_list);
-        scatter_copy_out(q, len[1], off[1], pos[1], lane, point_list);
-    } else {
-        // very large splats: the unit's output does not fit the staging buffer
-        scatter_walk<3>(ui, keys, vals, s_item, lane, pos[0], pos[1], point_list);
+    const uint32_t bit = 1u << lane;
+    const int my_row0 = lane >> 3, my_row1 = 4 + (lane >> 3);
+    const uint32_t total = pre_row(8), half = pre_row(4);
+    int r0 = 0;
+    while (r0 < 8) {                                    // warp-uniform
+        const uint32_t start = pre_row(r0);
+        int r1;
+        if (r0 == 0 && total <= (uint32_t)SQ_ENTRIES) r1 = 8;                                    // everything at once
+        else if ((r0 == 0 || r0 == 4) && half <= (uint32_t)SQ_ENTRIES && total - half <= (uint32_t)SQ_ENTRIES)
+            r1 = r0 + 4;                                                                         // tile halves
+        else {
+            r1 = r0 + 1;
+            while (r1 < 8 && pre_row(r1 + 1) - start <= (uint32_t)SQ_ENTRIES) ++r1;
+        }
+        if (pre_row(r1) != start) {                     // the group has output
+            const bool in0 = my_row0 >= r0 && my_row0 < r1, in1 = my_row1 >= r0 && my_row1 < r1;
+            const uint32_t off0 = pre[0] - start, off1 = pre[1] - start;
+            const uint32_t b0 = in0 ? bit : 0u, b1 = in1 ? bit : 0u;
+            const uint32_t a0 = q_addr + 4u * off0, a1 = q_addr + 4u * off1;
+            if (r1 <= 4) scatter_walk<true, false>(ui, keys, vals, s_item, lane, b0, b1, a0, a1);
+            else if (r0 >= 4) scatter_walk<false, true>(ui, keys, vals, s_item, lane, b0, b1, a0, a1);
+            else scatter_walk<true, true>(ui, keys, vals, s_item, lane, b0, b1, a0, a1);
+            scatter_copy_out(q, in0 ? len[0] : 0u, off0, pos[0], lane, point_list);
+            scatter_copy_out(q, in1 ? len[1] : 0u, off1, pos[1], lane, point_list);
+            __syncwarp();
+        }
+        r0 = r1;
     }
 }
 
