@@ -142,18 +142,20 @@ def path_bytes(P, V, R, N, sh_M):
     return B_fwd, B_bwd
 
 
-def stage_bytes(P, V, R, N, T, sh_M, visited):
+def stage_bytes(P, V, R, N, T, sh_M, visited, N1=0):
     """Algorithmic bytes per stage (DESIGN.md "kernels" table).  `visited` = sum over tiles of the instances the
-    composite actually walks (<= R; the rest of each tile's list is occluded and never read)."""
+    composite actually walks (<= R; the rest of each tile's list is occluded and never read); N1 = coarse items."""
     col = 12 if sh_M == 0 else 12 * sh_M
     return {
         "preprocess_fwd": P * (44 + (0 if sh_M == 0 else col) + 4 + 4 + 8 + 8) + V * (32 + 4),
-        "depth_sort": P * 8 * 2,                 # one read + one write of the (key, id) pairs
-        "offset_scan": P * (4 + 4 + 4),
-        "emit_cells": P * (4 + 8 + 4),
-        "cell_sort": 0, "cell_count": 0, "tile_offsets": 0,   # coarse-item passes (a few bytes per Gaussian; filled below)
-        "tile_scatter": R * 4,                   # the per-tile instance list itself
-        "_tile_ranges": T * 8,
+        "depth_sort": P * 16 * 4 + P * 24,       # 4 passes, each one read + one write of the (key, id) pairs; last pass
+                                                 # also delivers cell counts + rectangles in depth order
+        "offset_scan": P * 8,
+        "emit_cells": P * (4 + 8 + 4) + N1 * 8,
+        "cell_sort": N1 * 16,                    # one pass over the coarse items (<= 256 cells)
+        "cell_count": N1 * 4,
+        "tile_offsets": T * 16,
+        "tile_scatter": R * 4 + N1 * 8,          # the per-tile instance list itself + one read of the coarse items
         "render_fwd": visited * (4 + 32 + 12) + N * (8 + 12 + 4 + 4) + T * 8,
         "render_bwd": visited * (4 + 32 + 12 + 48) + N * (8 + 12 + 4 + 4) + T * 8,
         "preprocess_bwd": P * (4 + 44 + 56 + 12) + V * (48 + 32),
@@ -401,7 +403,8 @@ def main():
                 counts={"P": P, "V": V, "R": int(R), "N": N, "tiles": T, "visited_instances": visited,
                         "sum_n_contrib": blended_sum})
     if world == 1:
-        sb = stage_bytes(P, V, R, N, T, sh_M, visited)
+        N1 = int(_C.stats(state["geom"], P, sh_M).get("num_coarse", 0))
+        sb = stage_bytes(P, V, R, N, T, sh_M, visited, N1)
         stages = {k: {"ms": stage_ms[k], "alg_bytes": int(sb[k]), "gbs": sb[k] / (stage_ms[k] * 1e-3) / 1e9,
                       "frac_of_hbm_peak": sb[k] / (stage_ms[k] * 1e-3) / 1e9 / peak} for k in stage_ms if k in sb}
         dom = max(stages, key=lambda k: stages[k]["ms"])

@@ -140,7 +140,7 @@ typedef struct GsrStats {
     int      num_rendered;        /* R: (Gaussian, tile) instances                          */
     int      num_visible;         /* V: Gaussians with radii > 0                            */
     int      num_tiles;           /* tiles in the shard                                     */
-    int      reserved;
+    int      num_coarse;          /* N1: (Gaussian, 8x8-tile cell) items of the two-level binning */
 } GsrStats;
 
 int         gsr_abi_version(void);

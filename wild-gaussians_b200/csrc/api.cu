@@ -484,12 +484,14 @@ int gsr_get_stats(const void* geom_buffer, int P, int M, void* stream, GsrStats*
     carve_geom((char*)geom_buffer, P, M, &g);
     int32_t c[8];
     cudaStream_t s = (cudaStream_t)stream;
+    uint32_t n1 = 0;
     GSR_CUDA(cudaMemcpyAsync(c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA(cudaMemcpyAsync(&n1, g.offsets + P, sizeof(n1), cudaMemcpyDeviceToHost, s));
     GSR_CUDA(cudaStreamSynchronize(s));
     out->num_visible = c[1];
     out->num_rendered = c[2];   // low word of the 64-bit instance counter
     out->num_tiles = 0;
-    out->reserved = 0;
+    out->num_coarse = (int)n1;
     return 0;
 }
 

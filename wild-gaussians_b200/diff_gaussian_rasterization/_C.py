@@ -50,7 +50,7 @@ class GsrBackwardArgs(Structure):
 
 
 class GsrStats(Structure):
-    _fields_ = [("num_rendered", c_int), ("num_visible", c_int), ("num_tiles", c_int), ("reserved", c_int)]
+    _fields_ = [("num_rendered", c_int), ("num_visible", c_int), ("num_tiles", c_int), ("num_coarse", c_int)]
 
 
 def _load():
@@ -422,7 +422,7 @@ def debug_views(geomBuffer, binningBuffer, imgBuffer, P, M, W, H, R):
 def stats(geomBuffer, P, M):
     s = GsrStats()
     _check(_lib.gsr_get_stats(geomBuffer.data_ptr(), P, M, _stream(geomBuffer.device), byref(s)), "gsr_get_stats")
-    return {"num_rendered": s.num_rendered, "num_visible": s.num_visible}
+    return {"num_rendered": s.num_rendered, "num_visible": s.num_visible, "num_coarse": s.num_coarse}
 
 
 def profile_enable(on: bool) -> None:
