@@ -285,7 +285,9 @@ def main():
             "data": "synthetic (seeded, SURVEY.md 8d generator)",
             "config": {"workload": workload, "P": P, "W": W, "H": H, "tiles": T,
                        "l2": "inputs_larger_than_l2 (per-step working set >= 0.5 GB vs 126 MB L2)",
-                       "parallelism": "single GPU" if world == 1 else f"tile-row bands x{world}, NCCL all-gather (image) + all-reduce (partials)"}}
+                       "parallelism": "single GPU" if world == 1 else f"tile-row bands x{world}, NCCL all-gather (image) + " + (
+                           "all-reduce (partials)" if os.environ.get("GSR_PEER_REDUCE", "1") == "0" else
+                           "reduction fused into the backward composite over peer/multicast memory")}}
 
     sampler = ClockSampler(local_rank)
 
@@ -351,8 +353,7 @@ def main():
             fT = img[off:off + 4 * N].view(torch.float32).view(1, H, W)
             full = parallel.gather_image_bands(torch.cat([color, fT], 0), bands)
             bargs = backward_args(d, radii, geom, R, binning, img)
-            accum = _C.rasterize_gaussians_backward_partials(*bargs)
-            parallel.reduce_partials(accum[: P * 12])
+            accum = parallel.reduced_partials(bargs, P, dev)
             grads = _C.rasterize_gaussians_backward_finalize(accum, *bargs)
             _C.set_tile_row_shard(0, 0)
             state.update(R=R, radii=radii, geom=geom, binning=binning, img=img)

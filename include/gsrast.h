@@ -179,6 +179,15 @@ int    gsr_backward(const GsrBackwardArgs* args, void* stream);
  *   finalize: per-Gaussian chain rule from accum_scratch to every output tensor                     */
 int    gsr_backward_partials(const GsrBackwardArgs* args, void* stream);
 int    gsr_backward_finalize(const GsrBackwardArgs* args, void* stream);
+/* Reduction-fused variant of gsr_backward_partials for ranks that share a symmetric accumulator (one [P][12] fp32
+ * array per rank, each mapped into every process; NVLink/NVSwitch peer memory): the per-tile backward composite adds
+ * its sums directly into the accumulators of ALL ranks -- through `multicast_accum` (NVSwitch multicast address: one
+ * multimem.red per 16 bytes, the switch updates every replica) when it is non-NULL, else through the `n_peers` device
+ * pointers stored in the DEVICE array `peer_accum_dev`.  The arrays must have been zeroed on every rank (and a
+ * barrier passed) before any rank calls this; after a second barrier every rank holds the complete sums and calls
+ * gsr_backward_finalize with accum_scratch = its own array.  Replaces partials + all-reduce.                       */
+int    gsr_backward_partials_peers(const GsrBackwardArgs* args, const void* const* peer_accum_dev, int n_peers,
+                                   void* multicast_accum, void* stream);
 
 /* -- markVisible (rasterizer_impl.cu:54-66,141-153): present[i] = (view*p).z > 0.2 ------- */
 int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix,

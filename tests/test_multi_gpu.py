@@ -15,8 +15,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, peer_mode=0):
     import sys
+    os.environ["GSR_PEER_REDUCE"] = str(peer_mode)     # read when parallel.py is imported
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (root, os.path.join(root, "wild-gaussians_b200"), os.path.join(root, "tests", "golden")):
         if p not in sys.path:
@@ -58,7 +59,10 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_equals_single_gpu():
+@pytest.mark.parametrize("peer_mode", [0, 1, 2], ids=["nccl_allreduce", "peer_red", "multicast_red"])
+def test_sharded_equals_single_gpu(peer_mode):
+    """peer_mode 0: NCCL all-reduce of the partial gradients; 1 / 2: the reduction fused into the backward composite
+    through peer pointers / the NVSwitch multicast address (symmetric memory)."""
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -67,10 +71,10 @@ def test_sharded_equals_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, peer_mode)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
+    res = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(60)
         assert p.exitcode == 0

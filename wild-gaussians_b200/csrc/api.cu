@@ -387,7 +387,7 @@ static BwdAccum* accum_of(const GsrBackwardArgs* a) {
     return accum;
 }
 
-int gsr_backward_partials(const GsrBackwardArgs* a, void* stream) {
+static int backward_partials_impl(const GsrBackwardArgs* a, void* stream, const PeerAccum* peer) {
     int rc = check_bwd_args(a, true, false);
     if (rc || a->P == 0) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -401,16 +401,32 @@ int gsr_backward_partials(const GsrBackwardArgs* a, void* stream) {
     int ty0, ty1;
     shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
     BwdAccum* accum = accum_of(a);
-    GSR_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * sizeof(BwdAccum), s));
+    // with peer accumulators the caller zeroes them (all ranks, then a barrier) before any rank adds into them
+    if (!peer) GSR_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * sizeof(BwdAccum), s));
     const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
     if (a->R > 0) {
         prof_begin(ST_RENDER_BWD, s);
-        rc = launch_render_bwd(*a, g, b, im, colors, accum, ty0, ty1, s);
+        rc = launch_render_bwd(*a, g, b, im, colors, accum, ty0, ty1, s, peer);
         if (rc) return rc;
         GSR_STAGE(s, dbg, "render_bwd_kernel");
         prof_end(ST_RENDER_BWD, s);
     }
     return 0;
+}
+
+int gsr_backward_partials(const GsrBackwardArgs* a, void* stream) { return backward_partials_impl(a, stream, nullptr); }
+
+int gsr_backward_partials_peers(const GsrBackwardArgs* a, const void* const* peer_accum_dev, int n_peers,
+                                void* multicast_accum, void* stream) {
+    if ((!peer_accum_dev || n_peers <= 0) && !multicast_accum) {
+        set_error("gsr_backward_partials_peers needs peer pointers or a multicast address");
+        return GSR_E_INVALID;
+    }
+    PeerAccum peer;
+    peer.peers = multicast_accum ? nullptr : peer_accum_dev;
+    peer.n_peers = multicast_accum ? 0 : n_peers;
+    peer.multicast = multicast_accum;
+    return backward_partials_impl(a, stream, &peer);
 }
 
 int gsr_backward_finalize(const GsrBackwardArgs* a, void* stream) {

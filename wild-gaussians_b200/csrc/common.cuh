@@ -141,8 +141,15 @@ int launch_render_fwd(const GsrForwardArgs& a, const GeomState& g, const BinStat
 struct BwdAccum { float4 a, b, c; };  // per-Gaussian packed partial gradients (48 B)
 // a = {dmean2D.x, dmean2D.y, |dmean2D|, dconic.x}  b = {dconic.y, dconic.w, dopacity, dcolor.r}
 // c = {dcolor.g, dcolor.b, -, -}
+// accumulators of all ranks (symmetric memory) for the reduction-fused sharded backward; see render_bwd.cu
+struct PeerAccum {
+    const void* const* peers;   // device array of n_peers device pointers, or NULL
+    int n_peers;
+    void* multicast;            // multicast address, or NULL
+};
 int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinState& b, const ImgState& im,
-                      const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s);
+                      const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s,
+                      const PeerAccum* peer = nullptr);
 int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, const BwdAccum* accum, cudaStream_t s);
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);

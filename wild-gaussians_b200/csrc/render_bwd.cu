@@ -37,10 +37,45 @@ struct RenderBwdParams {
     const uint32_t* n_contrib;
     const float* dL_dpix;
     float* accum;   // [P][12]
+    // Tile-row sharded (multi-GPU) backward fused with its reduction: instead of the local array, the per-(tile,
+    // Gaussian) sums are added straight into the accumulators of ALL ranks -- one multimem.red per 16 bytes through
+    // the NVSwitch multicast address `mc` (the switch applies the add to every replica), or one red per peer when
+    // only peer pointers are available.  No all-reduce follows.
+    float* const* peers;   // [n_peers] device array of the ranks' accumulators mapped into this process, or NULL
+    int n_peers;
+    float* mc;             // multicast address of the same symmetric buffer, or NULL
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void multimem_red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+                 "f"(d) : "memory");
+}
+// add one Gaussian's 12-float row of sums to the accumulator(s)
+template <bool PEER>
+__device__ __forceinline__ void flush_row(const RenderBwdParams& p, size_t row, float4 A, float4 B, float4 C) {
+    const size_t off = row * RB_ACC;
+    if (PEER) {
+        if (p.mc != nullptr) {
+            multimem_red_add_v4(p.mc + off + 0, A.x, A.y, A.z, A.w);
+            multimem_red_add_v4(p.mc + off + 4, B.x, B.y, B.z, B.w);
+            multimem_red_add_v4(p.mc + off + 8, C.x, C.y, C.z, C.w);
+        } else {
+            for (int r = 0; r < p.n_peers; ++r) {
+                float* dst = p.peers[r] + off;
+                red_add_v4(dst + 0, A.x, A.y, A.z, A.w);
+                red_add_v4(dst + 4, B.x, B.y, B.z, B.w);
+                red_add_v4(dst + 8, C.x, C.y, C.z, C.w);
+            }
+        }
+    } else {
+        float* dst = p.accum + off;
+        red_add_v4(dst + 0, A.x, A.y, A.z, A.w);
+        red_add_v4(dst + 4, B.x, B.y, B.z, B.w);
+        red_add_v4(dst + 8, C.x, C.y, C.z, C.w);
+    }
 }
 
 // Sum 10 per-lane values over the 32 lanes of the warp with a multi-value butterfly: at every step a
@@ -297,10 +332,8 @@ __global__ void __launch_bounds__(PixelMap<PPT>::THREADS) render_bwd_kernel(cons
                     const float gx = -o * ddelx_dx * (con_o.x * a0.x + con_o.y * a0.y);
                     const float gy = -o * ddely_dy * (con_o.z * a0.y + con_o.y * a0.x);
                     const float h = -0.5f * o;
-                    float* dst = p.accum + (size_t)s_id[slot] * RB_ACC;
-                    red_add_v4(dst + 0, gx, gy, a0.z, h * a0.w);
-                    red_add_v4(dst + 4, h * a1.x, h * a1.y, a1.z, a1.w);
-                    red_add_v4(dst + 8, a2.x, a2.y, 0.f, 0.f);
+                    flush_row<false>(p, s_id[slot], make_float4(gx, gy, a0.z, h * a0.w), make_float4(h * a1.x, h * a1.y, a1.z, a1.w),
+                              make_float4(a2.x, a2.y, 0.f, 0.f));
                 }
             }
         }
@@ -326,6 +359,7 @@ struct __align__(16) PairRec {      // 80 bytes per staged Gaussian
 __device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
 
+template <bool PEER>
 __global__ void __launch_bounds__(128) render_bwd_packed_kernel(const __grid_constant__ RenderBwdParams p) {
     using PM = PixelMap<2>;
     constexpr int THREADS = PM::THREADS;   // 128
@@ -504,10 +538,8 @@ __global__ void __launch_bounds__(128) render_bwd_packed_kernel(const __grid_con
                 const float gx = -o * ddelx_dx * (A * a0.x + B * a0.y);
                 const float gy = -o * ddely_dy * (C * a0.y + B * a0.x);
                 const float h = -0.5f * o;
-                float* dst = p.accum + (size_t)s_id[tid] * RB_ACC;
-                red_add_v4(dst + 0, gx, gy, a0.z, h * a0.w);
-                red_add_v4(dst + 4, h * a1.x, h * a1.y, a1.z, a1.w);
-                red_add_v4(dst + 8, a2.x, a2.y, 0.f, 0.f);
+                flush_row<PEER>(p, s_id[tid], make_float4(gx, gy, a0.z, h * a0.w), make_float4(h * a1.x, h * a1.y, a1.z, a1.w),
+                          make_float4(a2.x, a2.y, 0.f, 0.f));
             }
         }
     }
@@ -528,8 +560,11 @@ static int bwd_ppt() {
 }
 
 int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinState& b, const ImgState& im,
-                      const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s) {
+                      const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s, const PeerAccum* peer) {
     RenderBwdParams p;
+    p.peers = peer ? (float* const*)(peer->peers) : nullptr;
+    p.n_peers = peer ? peer->n_peers : 0;
+    p.mc = peer ? reinterpret_cast<float*>(peer->multicast) : nullptr;
     p.W = a.W; p.H = a.H; p.grid_x = tiles_x(a.W); p.ty0 = ty0;
     p.ranges = im.ranges; p.point_list = b.point_list;
     p.subpixel_offset = reinterpret_cast<const float2*>(a.subpixel_offset);
@@ -543,8 +578,13 @@ int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinSta
         const char* e = getenv("GSR_BWD_PACKED");     // tuning aid: 1 = 2 pixels/lane in paired fp32 instructions
         packed = e ? atoi(e) : 1;
     }
+    if (peer) {   // the reduction-fused flush exists in the packed kernel only
+        render_bwd_packed_kernel<true><<<grid, 128, 0, s>>>(p);
+        count_launches(1);
+        return 0;
+    }
     if (packed) {
-        render_bwd_packed_kernel<<<grid, 128, 0, s>>>(p);
+        render_bwd_packed_kernel<false><<<grid, 128, 0, s>>>(p);
         count_launches(1);
         return 0;
     }

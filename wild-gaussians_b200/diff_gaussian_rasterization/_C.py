@@ -71,6 +71,7 @@ def _load():
     lib.gsr_backward.argtypes = [POINTER(GsrBackwardArgs), c_void_p]
     lib.gsr_backward_partials.argtypes = [POINTER(GsrBackwardArgs), c_void_p]
     lib.gsr_backward_finalize.argtypes = [POINTER(GsrBackwardArgs), c_void_p]
+    lib.gsr_backward_partials_peers.argtypes = [POINTER(GsrBackwardArgs), c_void_p, c_int, c_void_p, c_void_p]
     lib.gsr_mark_visible.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsr_img_views.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
     lib.gsr_binning_views.argtypes = [c_void_p, c_int, POINTER(c_void_p)]
@@ -85,6 +86,7 @@ def _load():
     lib.gsr_launch_count.restype = ctypes.c_ulonglong
     for name in ("gsr_forward_sizes", "gsr_forward_geometry", "gsr_binning_sizes", "gsr_forward_render",
                  "gsr_forward_recolor", "gsr_backward", "gsr_backward_partials", "gsr_backward_finalize",
+                 "gsr_backward_partials_peers",
                  "gsr_mark_visible", "gsr_img_views", "gsr_binning_views",
                  "gsr_geom_views", "gsr_get_stats"):
         getattr(lib, name).restype = c_int
@@ -274,7 +276,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rotations, scale_modifier,
                    cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
                    dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug,
-                   want_cov3D=True):
+                   want_cov3D=True, peer=None):
     """mode: "both" (gsr_backward), "partials" (returns the [P,12] accumulator), "finalize" (consumes it).
     want_cov3D=False (autograd path with scales/rotations): dL_dcov3D is an intermediate nobody reads, so it
     is neither allocated nor written (24 B per Gaussian) and None is returned in its place."""
@@ -332,6 +334,11 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
             a.dL_dsh = _ptr(dL_dsh)
             a.dL_dscale = dL_dscales.data_ptr() if have_scales else None
             a.dL_drot = dL_drotations.data_ptr() if have_scales else None
+        if peer is not None:
+            peers_dev, n_peers, mc = peer
+            _check(_lib.gsr_backward_partials_peers(byref(a), peers_dev or None, int(n_peers), mc or None, _stream(dev)),
+                   "gsr_backward_partials_peers")
+            return accum
         fn = {"both": _lib.gsr_backward, "partials": _lib.gsr_backward_partials,
               "finalize": _lib.gsr_backward_finalize}[mode]
         _check(fn(byref(a), _stream(dev)), "gsr_backward" + ("" if mode == "both" else "_" + mode))
@@ -361,6 +368,14 @@ def rasterize_gaussians_backward_partials(*args):
     """First half of the backward for the tile-row sharded path: this shard's per-Gaussian partial sums as a
     flat fp32 tensor whose first ``P*12`` entries are the ``[P,12]`` accumulator (same 23 arguments)."""
     return _backward_impl("partials", None, *args)
+
+
+def rasterize_gaussians_backward_partials_peers(accum, peers_dev_ptr, n_peers, multicast_ptr, *args):
+    """Reduction-fused first half (``gsr_backward_partials_peers``): this shard's sums are added directly into the
+    accumulators of all ranks.  ``accum`` is this rank's symmetric buffer (zeroed on every rank, barrier passed);
+    ``peers_dev_ptr`` the address of the DEVICE array holding the ranks' buffer pointers, ``multicast_ptr`` the
+    NVSwitch multicast address of the buffer or 0."""
+    return _backward_impl("partials", accum, *args, peer=(int(peers_dev_ptr), int(n_peers), int(multicast_ptr)))
 
 
 def rasterize_gaussians_backward_finalize(accum, *args):

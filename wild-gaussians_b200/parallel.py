@@ -17,6 +17,8 @@ The collective helpers below are backend-agnostic (tested with gloo on CPU, worl
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Sequence, Tuple
 
 import torch
@@ -83,6 +85,62 @@ def reduce_partials(accum: torch.Tensor, group=None) -> torch.Tensor:
     return accum
 
 
+# ---- reduction fused into the backward composite (peer / multicast memory over NVLink-NVSwitch) -----------------
+# GSR_PEER_REDUCE=1 (default): every rank's backward composite adds its per-Gaussian sums straight into the accumulators
+# of all ranks through peer pointers (torch symmetric memory over NVLink); =2: through the NVSwitch multicast address
+# when the platform offers one (one multimem.red per 16 bytes, the switch updates every replica); =0: NCCL all-reduce
+# of the partial arrays after the kernel.  Measured at C3 (profiles/): 2 GPUs 1.65 (NCCL) / 1.35 (peer) / 1.42 ms
+# (multicast); 4 GPUs 1.46 / 1.13 / 1.19 ms.  If symmetric memory cannot be set up the NCCL path is used.
+_PEER_MODE = int(os.environ.get("GSR_PEER_REDUCE", "1"))
+_peer_state: dict = {}
+_peer_warned = False
+
+
+def _peer_accumulator(P: int, device, group):
+    """This rank's symmetric [P,12] fp32 accumulator (+ handle), created once per (P, device, group)."""
+    import torch.distributed._symmetric_memory as symm_mem
+    key = (int(P), str(device), id(group))
+    st = _peer_state.get(key)
+    if st is None:
+        t = symm_mem.empty(P * 12 + 64, dtype=torch.float32, device=device)
+        hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+        mc = 0
+        if _PEER_MODE >= 2:
+            try:
+                mc = int(hdl.multicast_ptr or 0)
+            except Exception:
+                mc = 0
+        assert t.data_ptr() % 256 == 0 and all(int(x) % 256 == 0 for x in hdl.buffer_ptrs)
+        st = _peer_state[key] = (t, hdl, mc)
+    return st
+
+
+def reduced_partials(bwd_args, P: int, device, group=None) -> torch.Tensor:
+    """Backward composite of this rank's band + sum over all bands: returns the accumulator holding the complete
+    per-Gaussian sums (flat fp32, first P*12 entries).  Either NCCL all-reduce of the partial arrays or, with
+    GSR_PEER_REDUCE, the reduction fused into the kernel through peer / multicast memory."""
+    from diff_gaussian_rasterization import _C
+    st = None
+    if _PEER_MODE > 0 and P > 0 and dist.get_backend(group) == "nccl":
+        try:
+            st = _peer_accumulator(P, device, group)
+        except Exception as e:                      # no symmetric memory on this platform / build: NCCL path
+            global _peer_warned
+            if not _peer_warned:
+                _peer_warned = True
+                print(f"[parallel] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce")
+    if st is not None:
+        accum, hdl, mc = st
+        accum.zero_()
+        hdl.barrier(channel=0)          # every rank's accumulator is clean before anyone adds into it
+        _C.rasterize_gaussians_backward_partials_peers(accum, hdl.buffer_ptrs_dev, hdl.world_size, mc, *bwd_args)
+        hdl.barrier(channel=1)          # all contributions have landed everywhere
+        return accum
+    accum = _C.rasterize_gaussians_backward_partials(*bwd_args)
+    reduce_partials(accum[: P * 12], group)
+    return accum
+
+
 class _ShardedRasterize(torch.autograd.Function):
     """Tile-row sharded counterpart of ``diff_gaussian_rasterization._RasterizeGaussians``."""
 
@@ -122,9 +180,7 @@ class _ShardedRasterize(torch.autograd.Function):
         prev = _C.get_tile_row_shard()
         _C.set_tile_row_shard(*ctx.bands[rank])
         try:
-            accum = _C.rasterize_gaussians_backward_partials(*args)
-            P = int(means3D.size(0))
-            reduce_partials(accum[: P * 12], ctx.group)
+            accum = reduced_partials(args, int(means3D.size(0)), means3D.device, ctx.group)
             (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot) = \
                 _C.rasterize_gaussians_backward_finalize(accum, *args)
         finally:
