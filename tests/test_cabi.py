@@ -71,3 +71,17 @@ def test_invalid_arguments_are_rejected_with_a_message():
     # P == 0 is legal and does nothing
     a0 = C.GsrForwardArgs(); a0.P, a0.W, a0.H = 0, 64, 64
     assert lib.gsr_forward_geometry(byref(a0), None, None, None, byref(R), byref(N1)) == 0 and R.value == 0
+
+
+def test_peer_reduction_entry_point_validates_its_arguments():
+    """gsr_backward_partials_peers: without peer pointers and without a multicast address there is nothing to reduce
+    into -- rejected with a message, before any CUDA call."""
+    import diff_gaussian_rasterization._C as C
+    lib = C._lib
+    b = C.GsrBackwardArgs()
+    b.P, b.W, b.H = 10, 64, 64
+    assert lib.gsr_backward_partials_peers(byref(b), None, 0, None, None) == -1
+    assert b"peer" in lib.gsr_last_error()
+    # with a (dummy) multicast address the ordinary argument checks apply next: required pointers are NULL
+    assert lib.gsr_backward_partials_peers(byref(b), None, 0, ctypes.c_void_p(256), None) == -1
+    assert b"NULL" in lib.gsr_last_error()
