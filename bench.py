@@ -40,6 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "wild-gaussians_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import synthetic  # noqa: E402
 
@@ -253,6 +254,7 @@ def main():
     ap.add_argument("--config", default="C3", choices=list(synthetic.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
 
@@ -477,6 +479,14 @@ def main():
             tp["what"] = "2 forwards (different colours, same geometry) + 2 backwards, device-timed"
             line["two_pass"] = tp
 
+    # BASELINE config 3's "full train step": the reference's own, unmodified wildgaussians/method.py
+    # (GaussianModel._render_internal: appearance MLP + SH colours in PyTorch, two rasterizer passes) + loss + backward
+    if world == 1 and not a.no_train_step and sh_M == 0:
+        try:
+            line["train_step"] = full_train_step(kw, dev, max(3, a.steps // 4), a.impl)
+        except Exception as e:          # reporting only: never lose the timing line
+            line["train_step"] = {"unavailable": f"{type(e).__name__}: {e}"}
+
     # e2e through the public API with host buffers
     if not a.no_e2e:
         sharded = None
@@ -495,6 +505,41 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     return 0
+
+
+def full_train_step(kw, dev, steps, impl="ours"):
+    """ms per step of `GaussianModel._render_internal` + loss + backward (unmodified wildgaussians/method.py from
+    baseline/_ref, see tests/wg_harness.py) on a cloud of the workload's size with SH degree 3 + 32-d appearance
+    embedding (BASELINE.json config 3), on this repo's rasterizer and on the reference's compiled CUDA core."""
+    import wg_harness as wh
+    m, Config = wh.import_method()
+    if m is None:
+        return {"unavailable": "reference python package not present (baseline/_ref)"}
+    import diff_gaussian_rasterization as ours
+    from oracle import ref_cuda
+    kw3 = dict(kw); kw3["sh_degree"] = 3
+    scene = synthetic.make_scene(**kw3)
+    model, cfg = wh.make_model(m, Config, scene, dev)
+    cam = wh.make_camera(scene)
+    H, W = scene["image_height"], scene["image_width"]
+    g = torch.Generator().manual_seed(5)
+    G1, G2 = torch.randn(3, H, W, generator=g).to(dev), torch.randn(3, H, W, generator=g).to(dev)
+    res = {"what": "unmodified wildgaussians/method.py GaussianModel._render_internal (appearance on, uncertainty off, two "
+                   "rasterizer passes) + (render*G1).sum() + (raw_render*G2).sum() + backward; CUDA events, ms per step",
+           "P": kw3["P"], "W": W, "H": H, "steps": steps}
+    arms = [("ours_ms", ours.GaussianRasterizer, ours.GaussianRasterizationSettings)]
+    if ref_cuda.available():
+        api = make_reference_api(ref_cuda)
+        arms.append(("reference_rasterizer_ms", api["GaussianRasterizer"], api["GaussianRasterizationSettings"]))
+    ours._C.set_geometry_cache(True)
+    try:
+        for name, rcls, scls in arms:
+            wh.use_backend(m, rcls, scls)
+            res[name] = time_steps(lambda: wh.train_step(model, cfg, cam, G1, G2), steps, 3, dev, 1)
+    finally:
+        wh.use_backend(m, ours.GaussianRasterizer, ours.GaussianRasterizationSettings)
+        ours._C.set_geometry_cache(False)
+    return res
 
 
 def make_reference_api(_C):

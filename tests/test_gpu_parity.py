@@ -92,6 +92,25 @@ REF_SCENES = [
 ]
 
 
+def check_grad(name, ours, ref, ref_again):
+    """Gradient bar tied to the reference's own noise: the reference accumulates with float atomics, so two runs of
+    it on the same inputs differ (`ref_noise`).  Ours must be within max(20 x that noise, 1e-5) of the tensor's largest
+    magnitude -- two orders tighter than BASELINE.json's 1e-3 -- and every entry above 1e-3 of the maximum must
+    also agree RELATIVELY within 2e-3 + the noise (small-gradient Gaussians are not hidden behind the largest one)."""
+    ours, ref, ref_again = ours.double(), ref.double(), ref_again.double()
+    scale = float(ref.abs().max()) + 1e-30
+    ours_err = float((ours - ref).abs().max()) / scale
+    ref_noise = float((ref_again - ref).abs().max()) / scale
+    assert ours_err <= max(20.0 * ref_noise, 1e-5), (name, ours_err, ref_noise)
+    assert ours_err < GRAD_TOL, (name, ours_err)
+    big = ref.abs() > 1e-3 * scale
+    if bool(big.any()):
+        noise_abs = (ref_again - ref).abs()
+        rel = ((ours - ref).abs()[big] - 20.0 * noise_abs[big]).clamp_min(0) / ref.abs()[big]
+        assert float(rel.max()) < 2e-3, (name, "per-element relative", float(rel.max()))
+    return ours_err, ref_noise
+
+
 @pytest.mark.parametrize("kw", REF_SCENES, ids=lambda k: f"P{k['P']}_{k['W']}x{k['H']}_s{k['seed']}")
 def test_against_compiled_reference(C, dev, kw):
     from oracle import ref_cuda
@@ -121,10 +140,7 @@ def test_against_compiled_reference(C, dev, kw):
     for n in GRAD_NAMES:
         if rg[n].numel() == 0:
             continue
-        scale = float(rg[n].abs().max()) + 1e-30
-        ours_err = float((o["grads"][n].view_as(rg[n]) - rg[n]).abs().max()) / scale
-        ref_noise = float((rg2[n] - rg[n]).abs().max()) / scale     # float-atomic order noise of the reference itself
-        assert ours_err < GRAD_TOL, (n, ours_err, ref_noise)
+        check_grad(n, o["grads"][n].view_as(rg[n]), rg[n], rg2[n])
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -382,3 +398,116 @@ def test_full_size_properties(C, dev, cfg):
     for n in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity"):
         if o["grads"][n].numel():
             assert float(o["grads"][n][~vis].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------------
+# the BENCHMARKED configurations, value-checked against the compiled reference (same process, same tensors)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", ["C2", "C3", "C5"])
+def test_benchmarked_config_against_compiled_reference(C, dev, cfg):
+    """BASELINE.json configs 2 (500k, 800x800, SH degree 3 in-kernel), 3 (3M, 1080p, colours precomputed -- the
+    bench.py workload) and 5 on one GPU (6M, 4096x2160): R, radii, the sorted instance list, the tile ranges and
+    n_contrib bit-exact; pixels within 1e-4; all gradient tensors within the noise-tied bar of check_grad."""
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libdgr_ref.so not present")
+    kw = dict(synthetic.CONFIGS[cfg]); kw["seed"] = 0
+    scene = synthetic.make_scene(**kw)
+    d = synthetic.to_device(scene, dev)
+    C.set_geometry_cache(False)
+    o = run_ours(C, d)
+    R, color, radii, geom, binning, img = ref_cuda.rasterize_gaussians(*call_args(d))
+    P = d["means3D"].shape[0]
+    rv = ref_cuda.debug_views(geom, binning, img, P, d["image_width"], d["image_height"], R)
+    v = o["views"]
+    assert o["R"] == R
+    assert torch.equal(o["radii"], radii)
+    assert torch.equal(v["ranges"], rv["ranges"])
+    assert torch.equal(v["point_list"], rv["point_list"]), "sorted instance list differs"
+    assert torch.equal(v["n_contrib"], rv["n_contrib"])
+    pix = float((o["color"] - color).abs().max())
+    assert pix <= PIX_TOL, pix
+    assert float((v["final_T"] - rv["final_T"]).abs().max()) <= PIX_TOL
+    bargs = backward_args(d, radii, geom, R, binning, img)
+    rg = dict(zip(GRAD_NAMES, ref_cuda.rasterize_gaussians_backward(*bargs)))
+    rg2 = dict(zip(GRAD_NAMES, ref_cuda.rasterize_gaussians_backward(*bargs)))
+    torch.cuda.synchronize()
+    for n in GRAD_NAMES:
+        if rg[n].numel() == 0 or (n == "dL_dcov3D"):     # dL_dcov3D is an intermediate with scales/rotations given
+            continue
+        check_grad(n, o["grads"][n].view_as(rg[n]), rg[n], rg2[n])
+    C.set_geometry_cache(True)
+
+
+def test_gsr_forward_through_the_allocation_callback(C, dev):
+    """gsr_forward() -- the single call INTEGRATION.md tells a maintainer to bind, with the C allocation callback
+    standing in for the reference's three resize lambdas (rasterize_points.cu:27-33,78-80) -- gives the same image,
+    radii and instance list as the staged entry points the Python shim uses."""
+    import ctypes
+    from ctypes import CFUNCTYPE, byref, c_int, c_size_t, c_void_p
+    scene = synthetic.make_scene(P=50_000, W=400, H=304, sh_degree=2, seed=51)
+    d = synthetic.to_device(scene, dev)
+    o = run_ours(C, d)
+    P, W, H, M = 50_000, 400, 304, d["shs"].shape[1]
+    a = C.GsrForwardArgs()
+    a.P, a.D, a.M, a.W, a.H = P, d["sh_degree"], M, W, H
+    out_color = torch.zeros((3, H, W), device=dev)
+    radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+    for name, key in (("background", "bg"), ("means3D", "means3D"), ("shs", "shs"), ("opacities", "opacities"),
+                      ("scales", "scales"), ("rotations", "rotations"), ("viewmatrix", "viewmatrix"),
+                      ("projmatrix", "projmatrix"), ("campos", "campos"), ("subpixel_offset", "subpixel_offset")):
+        setattr(a, name, d[key].contiguous().data_ptr())
+    a.scale_modifier, a.tan_fovx, a.tan_fovy, a.kernel_size = 1.0, d["tanfovx"], d["tanfovy"], d["kernel_size"]
+    a.out_color, a.radii = out_color.data_ptr(), radii.data_ptr()
+    bufs, calls = {}, []
+
+    @CFUNCTYPE(c_void_p, c_void_p, c_int, c_size_t)
+    def alloc(_ctx, which, nbytes):
+        calls.append((which, nbytes))
+        bufs[which] = torch.empty((int(nbytes) + 256,), dtype=torch.uint8, device=dev)
+        p = bufs[which].data_ptr()
+        return (p + 255) // 256 * 256
+
+    lib = C._lib
+    lib.gsr_forward.argtypes = [ctypes.POINTER(C.GsrForwardArgs), CFUNCTYPE(c_void_p, c_void_p, c_int, c_size_t), c_void_p,
+                                c_void_p, ctypes.POINTER(c_int)]
+    lib.gsr_forward.restype = c_int
+    R = c_int(0)
+    rc = lib.gsr_forward(byref(a), alloc, None, torch.cuda.current_stream(dev).cuda_stream, byref(R))
+    torch.cuda.synchronize()
+    assert rc == 0, lib.gsr_last_error()
+    assert sorted(w for w, _ in calls) == [0, 1, 2, 3]          # GEOM, BINNING, IMG, SCRATCH each asked once
+    assert R.value == o["R"]
+    assert torch.equal(out_color, o["color"]) and torch.equal(radii, o["radii"])
+    pl = c_void_p()
+    binning_ptr = (bufs[1].data_ptr() + 255) // 256 * 256
+    assert lib.gsr_binning_views(binning_ptr, R.value, byref(pl)) == 0
+    off = pl.value - bufs[1].data_ptr()
+    mine = bufs[1][off:off + 4 * R.value].view(torch.int32)
+    assert torch.equal(mine, o["views"]["point_list"])
+    # NULL callback is rejected with a message
+    assert lib.gsr_forward(byref(a), CFUNCTYPE(c_void_p, c_void_p, c_int, c_size_t)(0), None, None, byref(R)) == -1
+
+
+def test_geometry_cache_hits_with_a_non_contiguous_view_matrix(C, dev):
+    """wildgaussians/method.py:1516 passes `torch.tensor(...).transpose(0, 1).to(device)` -- a NON-contiguous view matrix
+    whose contiguous copy is a new tensor on every call.  The reuse is keyed on the caller's own tensor objects, so
+    the second composite of a step still hits; the caller's radii tensor is its own copy."""
+    scene = synthetic.make_scene(P=20_000, W=256, H=160, sh_degree=None, seed=44)
+    d = synthetic.to_device(scene, dev)
+    d["viewmatrix"] = d["viewmatrix"].t().contiguous().t()      # same values, transposed strides
+    d["projmatrix"] = d["projmatrix"].t().contiguous().t()
+    assert not d["viewmatrix"].is_contiguous()
+    C.set_geometry_cache(True)
+    C.clear_geometry_cache()
+    args = list(call_args(d))
+    h0 = C.geometry_cache_hits()
+    R1, c1, radii1, g1, b1, i1 = C.rasterize_gaussians(*args)
+    radii1.zero_()                                              # a caller scribbling over its radii ...
+    R2, c2, radii2, g2, b2, i2 = C.rasterize_gaussians(*args)
+    assert C.geometry_cache_hits() == h0 + 1
+    assert torch.equal(c1, c2) and int(radii2.max()) > 0        # ... does not corrupt the cached state
+    ref = run_ours(C, d)                                        # (its backward drops the cache entry)
+    assert torch.equal(ref["color"], c1) and torch.equal(ref["radii"], radii2)
+    R3, *_ = C.rasterize_gaussians(*args)
+    assert C.geometry_cache_hits() == h0 + 1                    # entry was released when the backward started

@@ -491,8 +491,11 @@ int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R, size_t N
     if (impl < 0) {
         const char* e = getenv("GSR_SCATTER");       // tuning aid: 0 = direct per-lane stores, 1 = shared-memory staged
         impl = e ? atoi(e) : 1;
-        cudaFuncSetAttribute(cell_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SMEM);
     }
+    // function attributes are per device / context: set it for the current device on every call (a process may
+    // rasterize on several GPUs), it is a cheap driver call
+    if (impl != 0)
+        GSR_CUDA(cudaFuncSetAttribute(cell_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SQ_SMEM));
     if (impl == 0)
         cell_scatter_kernel<<<(cap + 7) / 8, 256, 0, s>>>(keys, vals, bs.unit_base, bs.cell_range, num_cells, bs.M, bs.row_total,
                                                           cap, bs.tile_start, cells_x, gx, gy, point_list);

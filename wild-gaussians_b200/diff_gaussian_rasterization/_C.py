@@ -111,23 +111,22 @@ def get_tile_row_shard():
 
 
 # ---- geometry reuse across consecutive forward calls ------------------------------------------
-# One entry (the previous forward).  An entry is reused only if every geometry input is THE SAME tensor object with
-# the same version counter (no in-place modification since), on the same stream, with the same scalar settings.
-# The entry keeps those tensors alive, so their addresses cannot be recycled for other data.  Modifying a tensor
-# behind autograd's back (``x.data.add_(...)``) does not bump the version: set GSR_GEOM_CACHE=0 for such code.
+# One entry (the previous forward).  An entry is reused only if every geometry input is THE SAME tensor object the
+# caller passed last time (identity of the ORIGINAL objects, before any dtype / contiguity conversion -- method.py:1516
+# passes a transposed, non-contiguous view matrix whose contiguous copy is a new tensor on every call) with the same
+# version counter (no in-place modification since), on the same stream, with the same scalar settings.  The entry
+# keeps those tensors and their converted copies alive, so their addresses cannot be recycled for other data.
+# Modifying a tensor behind autograd's back (``x.data.add_(...)``, a raw kernel writing through data_ptr) does not
+# bump the version: call clear_geometry_cache() after such writes or set GSR_GEOM_CACHE=0.  The entry is dropped when
+# a backward pass starts (no further forward on this geometry can follow before the parameters change).
 _size_hint: dict = {}      # (P, W, H, shard) -> bytes of the binning / scratch buffers of the previous call
 _GEOM_CACHE_ON = os.environ.get("GSR_GEOM_CACHE", "1") != "0"
 _geom_cache: dict = {}
 
 
-def geo_key_tensors(*tensors):
-    return tuple(tensors)
-
-
-def _geometry_key(dev, stream, P, W, H, M, a, tensors):
-    return (str(dev), int(stream), P, W, H, M, float(a.scale_modifier), float(a.tan_fovx), float(a.tan_fovy),
-            float(a.kernel_size), int(a.prefiltered), int(a.debug), int(a.tile_y0), int(a.tile_y1),
-            tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors))
+def _geometry_key(dev, stream, P, W, H, M, scalars, shard, tensors):
+    return (str(dev), int(stream), P, W, H, M, tuple(scalars), tuple(shard),
+            tuple((id(t), t.data_ptr() if t.numel() else 0, t._version, tuple(t.shape)) for t in tensors))
 
 
 def set_geometry_cache(on: bool) -> None:
@@ -180,12 +179,34 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 
     Returns ``(num_rendered, out_color[3,H,W], radii[P] int32, geomBuffer, binningBuffer, imgBuffer)``.
     """
+    return rasterize_gaussians_shard(_shard, background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                                     cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size,
+                                     subpixel_offset, image_height, image_width, sh, degree, campos, prefiltered, debug)
+
+
+def _abi_shard(shard, H):
+    """(y0, y1) as the C ABI wants it: (0, 0) is its "whole image" sentinel, so an EMPTY band (a rank with no tile
+    rows) is expressed as the empty band below the last row."""
+    y0, y1 = int(shard[0]), int(shard[1])
+    if (y0, y1) == (0, 0):
+        return 0, 0
+    if y1 <= y0:
+        gy = (int(H) + 15) // 16
+        return gy, gy
+    return y0, y1
+
+
+def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                              cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
+                              image_height, image_width, sh, degree, campos, prefiltered, debug):
+    """``rasterize_gaussians`` restricted to the tile rows ``shard = (y0, y1)`` ((0, 0): whole image)."""
     if means3D.ndimension() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
         raise RuntimeError("diff_gaussian_rasterization (sm_100a build) needs CUDA tensors; there is no CPU path")
     dev = means3D.device
     P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+    shard = _abi_shard(shard, H)
     with torch.cuda.device(dev):
         byte = dict(dtype=torch.uint8, device=dev)
         if P == 0:
@@ -194,15 +215,35 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                     torch.zeros((P,), dtype=torch.int32, device=dev), e, e.clone(), e.clone())
         # every pixel of the rendered rows and every radii entry is written by the kernels: the reference's
         # zero-fills (rasterize_points.cu:67-68) are only needed for the rows a tile-row shard leaves out
-        alloc_img = torch.empty if _shard == (0, 0) else torch.zeros
+        alloc_img = torch.empty if shard == (0, 0) else torch.zeros
         out_color = alloc_img((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
-        radii = torch.empty((P,), dtype=torch.int32, device=dev)
         M = int(sh.size(1)) if sh.numel() != 0 else 0
+        stream = _stream(dev)
+        gb, ib = c_size_t(0), c_size_t(0)
+        _check(_lib.gsr_forward_sizes(P, M, W, H, byref(gb), byref(ib)), "gsr_forward_sizes")
 
-        keep = [_f32c(t, dev) for t in (background, means3D, colors, opacity, scales, rotations, cov3D_precomp,
-                                        viewmatrix, projmatrix, subpixel_offset, sh, campos)]
-        (background, means3D, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
-         subpixel_offset, sh, campos) = keep
+        # Geometry reuse (SURVEY.md 8f-1): wild-gaussians composites the SAME Gaussians two or three times per step
+        # with different colours (raw / appearance-toned / depth; method.py:1573-1631).  When every geometry input is
+        # the identical, unmodified tensor object of the previous call, projection, depth ordering and tile binning
+        # are not repeated: only the composite runs, on the previous call's geom / binning state.
+        geo_orig = (means3D, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, subpixel_offset)
+        scalars = (float(scale_modifier), float(tan_fovx), float(tan_fovy), float(kernel_size), int(bool(prefiltered)),
+                   int(bool(debug)))
+        geo_key = _geometry_key(dev, stream, P, W, H, M, scalars, shard, geo_orig)
+        hit = _geom_cache.get("entry") if (_GEOM_CACHE_ON and M == 0) else None
+        if hit is not None and not (hit["key"] == geo_key and all(
+                (x is y) or (x.numel() == 0 and y.numel() == 0)      # "absent" inputs are fresh empty tensors per call
+                for x, y in zip(hit["orig"], geo_orig))):
+            hit = None
+
+        if hit is not None:
+            (means3D, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, subpixel_offset) = hit["conv"]
+            background, colors, campos = (_f32c(t, dev) for t in (background, colors, campos))
+        else:
+            (background, means3D, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
+             subpixel_offset, sh, campos) = (_f32c(t, dev) for t in (
+                 background, means3D, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
+                 subpixel_offset, sh, campos))
 
         a = GsrForwardArgs()
         a.P, a.D, a.M, a.W, a.H = P, int(degree), M, W, H
@@ -213,38 +254,27 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         a.campos = _ptr(campos); a.tan_fovx = float(tan_fovx); a.tan_fovy = float(tan_fovy)
         a.kernel_size = float(kernel_size); a.subpixel_offset = _ptr(subpixel_offset)
         a.prefiltered = int(bool(prefiltered)); a.debug = int(bool(debug))
-        a.tile_y0, a.tile_y1 = _shard
-        a.out_color = out_color.data_ptr(); a.radii = radii.data_ptr()
+        a.tile_y0, a.tile_y1 = shard
+        a.out_color = out_color.data_ptr()
 
-        gb, ib = c_size_t(0), c_size_t(0)
-        _check(_lib.gsr_forward_sizes(P, M, W, H, byref(gb), byref(ib)), "gsr_forward_sizes")
-        stream = _stream(dev)
-
-        # Geometry reuse (SURVEY.md 8f-1): wild-gaussians composites the SAME Gaussians two or three times per step
-        # with different colours (raw / appearance-toned / depth; method.py:1573-1631).  When every geometry input is
-        # the identical, unmodified tensor object of the previous call, projection, depth ordering and tile binning
-        # are not repeated: only the composite runs, on the previous call's geom / binning state.
-        geo_key = _geometry_key(dev, stream, P, W, H, M, a, (means3D, opacity, scales, rotations, cov3D_precomp,
-                                                              viewmatrix, projmatrix, subpixel_offset))
-        hit = _geom_cache.get("entry") if (_GEOM_CACHE_ON and M == 0) else None
-        if hit is not None and hit["key"] == geo_key and all(
-                (x is y) or (x.numel() == 0 and y.numel() == 0)      # "absent" inputs are fresh empty tensors per call
-                for x, y in zip(hit["tensors"], geo_key_tensors(means3D, opacity, scales, rotations, cov3D_precomp,
-                                                                viewmatrix, projmatrix, subpixel_offset))):
+        if hit is not None:
             img2 = torch.empty((ib.value,), **byte)
             a.radii = hit["radii"].data_ptr()
             _check(_lib.gsr_forward_recolor(byref(a), hit["geom"].data_ptr(), hit["binning"].data_ptr(),
                                             hit["img"].data_ptr(), img2.data_ptr(), stream), "gsr_forward_recolor")
             _geom_cache["hits"] = _geom_cache.get("hits", 0) + 1
+            # the caller gets its own radii tensor: the cached one must survive in-place edits by the caller
             return hit["R"], out_color, hit["radii"].clone(), hit["geom"], hit["binning"], img2
 
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        a.radii = radii.data_ptr()
         geom = torch.empty((gb.value,), **byte)
         img = torch.empty((ib.value,), **byte)
         # The instance counts are known only after a device->host read-back inside gsr_forward_geometry.  To keep
         # the GPU idle gap behind that synchronisation short, the two count-sized buffers are allocated beforehand
         # from the sizes of the previous call with the same shape (training re-renders nearly the same scene) and
         # re-allocated only if they turn out too small.
-        hint_key = (P, W, H, _shard)
+        hint_key = (P, W, H, shard)
         hint = _size_hint.get(hint_key)
         binning = scratch = None
         if hint is not None:
@@ -266,17 +296,17 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         # allocation on this stream is ordered after the kernels that use it.
         del scratch
         if _GEOM_CACHE_ON and M == 0:
-            _geom_cache["entry"] = dict(key=geo_key, tensors=geo_key_tensors(means3D, opacity, scales, rotations,
-                                                                               cov3D_precomp, viewmatrix, projmatrix,
-                                                                               subpixel_offset),
-                                        R=R.value, radii=radii, geom=geom, binning=binning, img=img)
+            _geom_cache["entry"] = dict(
+                key=geo_key, orig=geo_orig,
+                conv=(means3D, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, subpixel_offset),
+                R=R.value, radii=radii.clone(), geom=geom, binning=binning, img=img)
     return R.value, out_color, radii, geom, binning, img
 
 
 def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rotations, scale_modifier,
                    cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
                    dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug,
-                   want_cov3D=True, peer=None):
+                   want_cov3D=True, peer=None, shard=None):
     """mode: "both" (gsr_backward), "partials" (returns the [P,12] accumulator), "finalize" (consumes it).
     want_cov3D=False (autograd path with scales/rotations): dL_dcov3D is an intermediate nobody reads, so it
     is neither allocated nor written (24 B per Gaussian) and None is returned in its place."""
@@ -284,6 +314,9 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
     P = int(means3D.size(0))
     H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
     M = int(sh.size(1)) if sh.numel() != 0 else 0
+    # a backward pass has started: no further forward on the cached geometry can follow before the parameters
+    # change, so the cache entry (one frame's geom / binning / img buffers) is released with the autograd graph
+    _geom_cache.pop("entry", None)
     with torch.cuda.device(dev):
         f32 = dict(dtype=torch.float32, device=dev)
         have_scales = scales.numel() != 0
@@ -324,7 +357,7 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
         a.subpixel_offset = _ptr(subpixel_offset); a.radii = radii.data_ptr()
         a.geom_buffer = _ptr(geomBuffer); a.binning_buffer = _ptr(binningBuffer); a.img_buffer = _ptr(imageBuffer)
         a.dL_dpix = _ptr(dL_dout_color); a.debug = int(bool(debug))
-        a.tile_y0, a.tile_y1 = _shard
+        a.tile_y0, a.tile_y1 = _abi_shard(_shard if shard is None else shard, H)
         a.accum_scratch = accum.data_ptr()
         if outs is not None:
             a.dL_dmean2D = dL_dmeans2D.data_ptr(); a.dL_dconic = None
@@ -364,23 +397,24 @@ def rasterize_gaussians_backward_lean(*args):
     return _backward_impl("both", None, *args, want_cov3D=False)
 
 
-def rasterize_gaussians_backward_partials(*args):
+def rasterize_gaussians_backward_partials(*args, shard=None):
     """First half of the backward for the tile-row sharded path: this shard's per-Gaussian partial sums as a
     flat fp32 tensor whose first ``P*12`` entries are the ``[P,12]`` accumulator (same 23 arguments)."""
-    return _backward_impl("partials", None, *args)
+    return _backward_impl("partials", None, *args, shard=shard)
 
 
-def rasterize_gaussians_backward_partials_peers(accum, peers_dev_ptr, n_peers, multicast_ptr, *args):
+def rasterize_gaussians_backward_partials_peers(accum, peers_dev_ptr, n_peers, multicast_ptr, *args, shard=None):
     """Reduction-fused first half (``gsr_backward_partials_peers``): this shard's sums are added directly into the
     accumulators of all ranks.  ``accum`` is this rank's symmetric buffer (zeroed on every rank, barrier passed);
     ``peers_dev_ptr`` the address of the DEVICE array holding the ranks' buffer pointers, ``multicast_ptr`` the
     NVSwitch multicast address of the buffer or 0."""
-    return _backward_impl("partials", accum, *args, peer=(int(peers_dev_ptr), int(n_peers), int(multicast_ptr)))
+    return _backward_impl("partials", accum, *args, peer=(int(peers_dev_ptr), int(n_peers), int(multicast_ptr)),
+                          shard=shard)
 
 
-def rasterize_gaussians_backward_finalize(accum, *args):
+def rasterize_gaussians_backward_finalize(accum, *args, shard=None):
     """Second half: per-Gaussian chain rule from the (all-reduced) accumulator to the 8 gradient tensors."""
-    return _backward_impl("finalize", accum, *args, want_cov3D=False)
+    return _backward_impl("finalize", accum, *args, want_cov3D=False, shard=shard)
 
 
 def mark_visible(means3D, viewmatrix, projmatrix):

@@ -115,7 +115,7 @@ def _peer_accumulator(P: int, device, group):
     return st
 
 
-def reduced_partials(bwd_args, P: int, device, group=None) -> torch.Tensor:
+def reduced_partials(bwd_args, P: int, device, group=None, shard=None) -> torch.Tensor:
     """Backward composite of this rank's band + sum over all bands: returns the accumulator holding the complete
     per-Gaussian sums (flat fp32, first P*12 entries).  Either NCCL all-reduce of the partial arrays or, with
     GSR_PEER_REDUCE, the reduction fused into the kernel through peer / multicast memory."""
@@ -133,10 +133,11 @@ def reduced_partials(bwd_args, P: int, device, group=None) -> torch.Tensor:
         accum, hdl, mc = st
         accum.zero_()
         hdl.barrier(channel=0)          # every rank's accumulator is clean before anyone adds into it
-        _C.rasterize_gaussians_backward_partials_peers(accum, hdl.buffer_ptrs_dev, hdl.world_size, mc, *bwd_args)
+        _C.rasterize_gaussians_backward_partials_peers(accum, hdl.buffer_ptrs_dev, hdl.world_size, mc, *bwd_args,
+                                                       shard=shard)
         hdl.barrier(channel=1)          # all contributions have landed everywhere
         return accum
-    accum = _C.rasterize_gaussians_backward_partials(*bwd_args)
+    accum = _C.rasterize_gaussians_backward_partials(*bwd_args, shard=shard)
     reduce_partials(accum[: P * 12], group)
     return accum
 
@@ -153,13 +154,16 @@ class _ShardedRasterize(torch.autograd.Function):
         args = (s.bg, means3D, colors_precomp, opacities, scales, rotations, s.scale_modifier, cov3Ds_precomp,
                 s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size, s.subpixel_offset,
                 s.image_height, s.image_width, sh, s.sh_degree, s.campos, s.prefiltered, s.debug)
-        prev = _C.get_tile_row_shard()
-        _C.set_tile_row_shard(*bands[rank])
-        try:
-            num_rendered, color, radii, geom, binning, img = _C.rasterize_gaussians(*args)
-        finally:
-            _C.set_tile_row_shard(*prev)
         H, W = int(s.image_height), int(s.image_width)
+        if int(means3D.size(0)) == 0:          # nothing to render (the reference skips everything, rasterize_points.cu:83)
+            ctx.empty = True
+            dev = means3D.device
+            z = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+            return z, torch.zeros((0,), dtype=torch.int32, device=dev), (torch.zeros((H, W), dtype=torch.float32, device=dev)
+                                                                         if s.return_accumulation else None)
+        ctx.empty = False
+        # the band is an explicit argument of the call (stored on ctx for the backward), not module state
+        num_rendered, color, radii, geom, binning, img = _C.rasterize_gaussians_shard(tuple(bands[rank]), *args)
         offset = (128 - img.data_ptr()) % 128
         final_T = img[offset:offset + 4 * H * W].view(torch.float32).view(1, H, W)
         full = gather_image_bands(torch.cat([color, final_T], dim=0), bands, group)
@@ -172,19 +176,17 @@ class _ShardedRasterize(torch.autograd.Function):
     def backward(ctx, grad_out_color, _1, _2):
         from diff_gaussian_rasterization import _C
         s = ctx.raster_settings
+        if ctx.empty:
+            return (None,) * 11
         colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img = ctx.saved_tensors
         args = (s.bg, means3D, radii, colors_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp,
                 s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size, s.subpixel_offset,
                 grad_out_color, sh, s.sh_degree, s.campos, geom, ctx.num_rendered, binning, img, s.debug)
         rank = dist.get_rank(ctx.group)
-        prev = _C.get_tile_row_shard()
-        _C.set_tile_row_shard(*ctx.bands[rank])
-        try:
-            accum = reduced_partials(args, int(means3D.size(0)), means3D.device, ctx.group)
-            (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot) = \
-                _C.rasterize_gaussians_backward_finalize(accum, *args)
-        finally:
-            _C.set_tile_row_shard(*prev)
+        shard = tuple(ctx.bands[rank])
+        accum = reduced_partials(args, int(means3D.size(0)), means3D.device, ctx.group, shard=shard)
+        (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot) = \
+            _C.rasterize_gaussians_backward_finalize(accum, *args, shard=shard)
         return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, None, None, None)
 
 
