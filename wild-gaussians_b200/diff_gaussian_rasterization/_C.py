@@ -126,7 +126,8 @@ _geom_cache: dict = {}
 
 def _geometry_key(dev, stream, P, W, H, M, scalars, shard, tensors):
     return (str(dev), int(stream), P, W, H, M, tuple(scalars), tuple(shard),
-            tuple((id(t), t.data_ptr() if t.numel() else 0, t._version, tuple(t.shape)) for t in tensors))
+            # "absent" inputs are fresh zero-element tensors on every call (__init__.py:218-228): they compare equal
+            tuple((id(t), t.data_ptr(), t._version, tuple(t.shape)) if t.numel() else None for t in tensors))
 
 
 def set_geometry_cache(on: bool) -> None:
