@@ -208,6 +208,52 @@ int gsr_geom_views(const void* geom_buffer, int P, int M, const float** depths,
                    const float** records, const uint32_t** tiles_touched, const float** rgb);
 int gsr_get_stats(const void* geom_buffer, int P, int M, void* stream, GsrStats* out);
 
+/* -- fused per-Gaussian colour op of wild-gaussians (optional entry points) ---------------------------
+ * Replaces, for sh_degree = 3 (48 SH features), 24 per-Gaussian embedding features and a 32-d image embedding, the
+ * PyTorch statements of wildgaussians/method.py that turn the model's features into the two colour sets the rasterizer
+ * composites: `features.clamp_max(1)` (:1570), eval_sh + 0.5 + clamp_min(0) for the raw colours (:1571-1579, :493-548),
+ * EmbeddingModel.forward (59 -> 128 -> 128 -> 6 MLP, x 0.01, affine on the features; :874-900) and the toned colours
+ * (:1586-1598).  The MLP runs on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).
+ *   1. gsr_appearance_pack_weights(): fp32 nn.Linear parameters + the image embedding -> packed bf16 operand image
+ *      (gsr_appearance_packed_weight_bytes() bytes, 16-byte aligned); once per step
+ *   2. gsr_appearance_colors_forward():  colors_raw (optional) and colors_toned, [P,3] each
+ *   3. gsr_appearance_colors_backward(): gradients of every per-Gaussian input; weight gradients are accumulated in
+ *      `grad_pack` (gsr_appearance_grad_pack_bytes() bytes, zeroed by the call)
+ *   4. gsr_appearance_unpack_grads():    grad_pack -> dW1 [128,59], db1 [128], dW2 [128,128], db2 [128], dW3 [6,128],
+ *      db3 [6], d(image embedding) [32]
+ * `status` (optional, device int, zero it first) becomes non-zero if an internal barrier wait timed out.              */
+typedef struct GsrAppearanceArgs {
+    int P;
+    int sh_degree;                    /* ACTIVE degree 0..3 (method.py: active_sh_degree); storage is always degree 3 */
+    const float* features_dc;         /* [P,3]   raw (unclamped) DC features                                          */
+    const float* features_rest;       /* [P,45]  raw higher-order features, coefficient-major (k, channel)            */
+    const float* embeddings;          /* [P,24]  per-Gaussian appearance features                                      */
+    const float* means3D;             /* [P,3]                                                                         */
+    const float* campos;              /* [3]                                                                           */
+    const void*  packed_weights;      /* from gsr_appearance_pack_weights                                              */
+    float* colors_raw;                /* [P,3] out, may be NULL                                                        */
+    float* colors_toned;              /* [P,3] out                                                                     */
+    /* backward only */
+    const float* dL_dcolors_raw;      /* [P,3] or NULL                                                                 */
+    const float* dL_dcolors_toned;    /* [P,3]                                                                         */
+    float* dL_dfeatures_dc;           /* [P,3]                                                                         */
+    float* dL_dfeatures_rest;         /* [P,45]                                                                        */
+    float* dL_dembeddings;            /* [P,24]                                                                        */
+    float* dL_dmeans3D;               /* [P,3]  through the view direction of the SH evaluation                        */
+    float* grad_pack;                 /* packed weight-gradient image                                                  */
+    int*   status;                    /* optional                                                                      */
+} GsrAppearanceArgs;
+
+size_t gsr_appearance_packed_weight_bytes(void);
+size_t gsr_appearance_grad_pack_bytes(void);
+int gsr_appearance_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                                const float* b3, const float* appearance_embedding, void* packed_weights, void* stream);
+int gsr_appearance_colors_forward(const GsrAppearanceArgs* args, void* stream);
+int gsr_appearance_colors_backward(const GsrAppearanceArgs* args, void* stream);
+int gsr_appearance_unpack_grads(const float* grad_pack, const float* W1, const float* appearance_embedding, float* dW1,
+                                float* db1, float* dW2, float* db2, float* dW3, float* db3,
+                                float* dappearance_embedding, void* stream);
+
 /* Optional per-stage device timing (cudaEvents on the caller's stream around each stage of the
  * next forward / backward calls).  The caller synchronises the stream, then reads the stage times of
  * the most recent calls in milliseconds (-1 for stages that did not run).  Not thread-safe.        */

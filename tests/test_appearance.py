@@ -1,0 +1,112 @@
+"""GPU parity of the fused colour op (csrc/appearance.cu, tcgen05) against (a) the golden vectors produced by the
+reference itself (tests/golden/colors_*.npz: outputs + autograd gradients of wildgaussians' EmbeddingModel / eval_sh in
+fp64) and (b) the torch restatement oracle/color_torch.py in fp32 on larger seeded inputs (raw + toned colours, every
+gradient incl. the mean through the view direction, ragged last tile).
+
+Bars: the MLP runs with bf16 operands (fp32 accumulation), so colours are compared at 3e-3 absolute and gradients at
+2e-2 of the tensor's largest magnitude (measured values are printed by -s); everything outside the MLP is fp32 and the
+raw colours (no MLP involved) must agree to 1e-5.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+COL_TOL, GRAD_TOL = 3e-3, 2e-2
+
+
+def _mlp(W1, b1, W2, b2, W3, b3, dev):
+    mlp = torch.nn.Sequential(torch.nn.Linear(59, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128), torch.nn.ReLU(),
+                              torch.nn.Linear(128, 6)).to(dev)
+    with torch.no_grad():
+        for lin, W, b in ((mlp[0], W1, b1), (mlp[2], W2, b2), (mlp[4], W3, b3)):
+            lin.weight.copy_(W); lin.bias.copy_(b)
+    return mlp
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / (float(b.abs().max()) + 1e-30)
+
+
+@pytest.mark.parametrize("name", ["colors_deg3", "colors_deg1"])
+def test_fused_colors_against_reference_golden(name):
+    import fused_colors as fc
+    dev = torch.device("cuda:0")
+    d = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    T = lambda k: torch.tensor(d[k], dtype=torch.float32, device=dev)
+    feats = T("features")
+    dc, rest = feats[:, :3].contiguous().requires_grad_(True), feats[:, 3:].contiguous().requires_grad_(True)
+    gemb, aemb = T("gembedding").requires_grad_(True), T("aembedding").requires_grad_(True)
+    mlp = _mlp(T("W1"), T("b1"), T("W2"), T("b2"), T("W3"), T("b3"), dev)
+    raw, toned = fc.fused_colors(dc, rest, gemb, aemb, mlp, T("means3D"), T("campos"), int(d["active_deg"]))
+    err = float((toned.detach() - T("colors")).abs().max())
+    assert err < COL_TOL, err
+    (toned * T("dL_dcolors")).sum().backward()
+    torch.cuda.synchronize()
+    g_feat = torch.cat([dc.grad, rest.grad], dim=1)
+    worst = {"features": _rel(g_feat, T("g_features")), "gembedding": _rel(gemb.grad, T("g_gembedding")),
+             "aembedding": _rel(aemb.grad, T("g_aembedding"))}
+    for i, lin in zip((1, 2, 3), (mlp[0], mlp[2], mlp[4])):
+        worst[f"W{i}"] = _rel(lin.weight.grad, T(f"g_W{i}"))
+        worst[f"b{i}"] = _rel(lin.bias.grad, T(f"g_b{i}"))
+    print(name, "colour err", err, "grad rel err", worst)
+    for k, v in worst.items():
+        assert v < GRAD_TOL, (k, v)
+
+
+@pytest.mark.parametrize("P,deg", [(100_037, 3), (4_096, 2), (77, 0)])
+def test_fused_colors_against_torch_oracle(P, deg):
+    import fused_colors as fc
+    from oracle import color_torch as ct
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1000 + P)
+    R = lambda *s, scale=1.0: (torch.randn(*s, generator=g) * scale).to(dev)
+    dc = ((torch.rand(P, 3, generator=g) * 1.6 - 0.9) / 0.28209479).to(dev)          # some colours clamp at 0, some features > 1
+    rest, gemb, aemb = R(P, 45, scale=0.3), R(P, 24, scale=0.5), R(32, scale=0.5)
+    means, campos = R(P, 3, scale=2.0), torch.tensor([0.1, -0.2, 0.3], device=dev)
+    torch.manual_seed(P)
+    mlp = torch.nn.Sequential(torch.nn.Linear(59, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128), torch.nn.ReLU(),
+                              torch.nn.Linear(128, 6)).to(dev)
+    with torch.no_grad():
+        mlp[4].bias[3:] = 100.0                   # a trained model has mul ~ 1 (tests/golden/make_golden_colors.py)
+    dLr, dLt = R(P, 3), R(P, 3)
+    leaves = [t.clone().requires_grad_(True) for t in (dc, rest, gemb, aemb, means)]
+    raw, toned = fc.fused_colors(leaves[0], leaves[1], leaves[2], leaves[3], mlp, leaves[4], campos, deg)
+    ((raw * dLr).sum() + (toned * dLt).sum()).backward()
+    ours = [t.grad.clone() for t in leaves] + [p.grad.clone() for p in mlp.parameters()]
+    for p in mlp.parameters():
+        p.grad = None
+    leaves2 = [t.clone().requires_grad_(True) for t in (dc, rest, gemb, aemb, means)]
+    lin = [mlp[0], mlp[2], mlp[4]]
+    raw2, toned2 = ct.colors(leaves2[0], leaves2[1], leaves2[2], leaves2[3], lin[0].weight, lin[0].bias, lin[1].weight,
+                             lin[1].bias, lin[2].weight, lin[2].bias, leaves2[4], campos, deg)
+    ((raw2 * dLr).sum() + (toned2 * dLt).sum()).backward()
+    ref = [t.grad for t in leaves2] + [p.grad for p in mlp.parameters()]
+    torch.cuda.synchronize()
+    e_raw, e_toned = float((raw - raw2).abs().max()), float((toned - toned2).abs().max())
+    assert e_raw < 1e-5, e_raw                                   # no MLP involved: fp32 on both sides
+    assert e_toned < COL_TOL, e_toned
+    names = ["features_dc", "features_rest", "embeddings", "app_embedding", "means3D", "W1", "b1", "W2", "b2", "W3", "b3"]
+    worst = {n: _rel(a, b) for n, a, b in zip(names, ours, ref)}
+    print(P, deg, "raw", e_raw, "toned", e_toned, worst)
+    for n, v in worst.items():
+        assert v < GRAD_TOL, (n, v)
+
+
+def test_fused_colors_rejects_other_shapes_and_cpu():
+    import fused_colors as fc
+    dev = torch.device("cuda:0")
+    mlp = torch.nn.Sequential(torch.nn.Linear(59, 128), torch.nn.ReLU(), torch.nn.Linear(128, 128), torch.nn.ReLU(),
+                              torch.nn.Linear(128, 6)).to(dev)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    with pytest.raises(RuntimeError, match="default shapes"):
+        fc.fused_colors(z(10, 3), z(10, 24), z(10, 24), z(32), mlp, z(10, 3), z(3), 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fc.fused_colors(torch.zeros(10, 3), torch.zeros(10, 45), torch.zeros(10, 24), torch.zeros(32), mlp.cpu(),
+                        torch.zeros(10, 3), torch.zeros(3), 3)

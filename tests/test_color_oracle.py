@@ -82,3 +82,22 @@ def test_reference_method_module_imports_on_the_drop_in_package():
     assert m.GaussianRasterizer is ours.GaussianRasterizer
     assert m.GaussianRasterizationSettings is ours.GaussianRasterizationSettings
     assert m.GaussianRasterizationSettings._fields[0] == "image_height" and len(m.GaussianRasterizationSettings._fields) == 15
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_torch_restatement_matches_the_reference_outputs_and_gradients(name):
+    """oracle/color_torch.py (the oracle of the fused CUDA colour op) in fp64 against the reference's own outputs and
+    autograd gradients."""
+    import torch
+    from oracle import color_torch as ct
+    d, w = _load(name)
+    t = {k: torch.tensor(d[k], dtype=torch.float64, requires_grad=True) for k in
+         ("features", "gembedding", "aembedding", "W1", "b1", "W2", "b2", "W3", "b3")}
+    f = t["features"]
+    raw, toned = ct.colors(f[:, :3], f[:, 3:], t["gembedding"], t["aembedding"], t["W1"], t["b1"], t["W2"], t["b2"], t["W3"],
+                           t["b3"], torch.tensor(d["means3D"]), torch.tensor(d["campos"]), int(d["active_deg"]))
+    assert float((toned.detach() - torch.tensor(d["colors"])).abs().max()) < 1e-12
+    (toned * torch.tensor(d["dL_dcolors"])).sum().backward()
+    for k, g in (("features", "g_features"), ("gembedding", "g_gembedding"), ("aembedding", "g_aembedding"), ("W1", "g_W1"),
+                 ("b1", "g_b1"), ("W2", "g_W2"), ("b2", "g_b2"), ("W3", "g_W3"), ("b3", "g_b3")):
+        assert float((t[k].grad - torch.tensor(d[g])).abs().max()) < 1e-10 * max(1.0, float(np.abs(d[g]).max())), k

@@ -49,6 +49,17 @@ class GsrBackwardArgs(Structure):
     ]
 
 
+class GsrAppearanceArgs(Structure):
+    _fields_ = [
+        ("P", c_int), ("sh_degree", c_int),
+        ("features_dc", c_void_p), ("features_rest", c_void_p), ("embeddings", c_void_p), ("means3D", c_void_p),
+        ("campos", c_void_p), ("packed_weights", c_void_p), ("colors_raw", c_void_p), ("colors_toned", c_void_p),
+        ("dL_dcolors_raw", c_void_p), ("dL_dcolors_toned", c_void_p), ("dL_dfeatures_dc", c_void_p),
+        ("dL_dfeatures_rest", c_void_p), ("dL_dembeddings", c_void_p), ("dL_dmeans3D", c_void_p),
+        ("grad_pack", c_void_p), ("status", c_void_p),
+    ]
+
+
 class GsrStats(Structure):
     _fields_ = [("num_rendered", c_int), ("num_visible", c_int), ("num_tiles", c_int), ("num_coarse", c_int)]
 
@@ -77,6 +88,15 @@ def _load():
     lib.gsr_binning_views.argtypes = [c_void_p, c_int, POINTER(c_void_p)]
     lib.gsr_geom_views.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
     lib.gsr_get_stats.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(GsrStats)]
+    lib.gsr_appearance_packed_weight_bytes.restype = c_size_t
+    lib.gsr_appearance_grad_pack_bytes.restype = c_size_t
+    lib.gsr_appearance_pack_weights.argtypes = [c_void_p] * 9
+    lib.gsr_appearance_colors_forward.argtypes = [POINTER(GsrAppearanceArgs), c_void_p]
+    lib.gsr_appearance_colors_backward.argtypes = [POINTER(GsrAppearanceArgs), c_void_p]
+    lib.gsr_appearance_unpack_grads.argtypes = [c_void_p] * 11
+    for name in ("gsr_appearance_pack_weights", "gsr_appearance_colors_forward", "gsr_appearance_colors_backward",
+                 "gsr_appearance_unpack_grads"):
+        getattr(lib, name).restype = c_int
     lib.gsr_profile_enable.argtypes = [c_int]
     lib.gsr_profile_enable.restype = None
     lib.gsr_profile_stage_count.restype = c_int
