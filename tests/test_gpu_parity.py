@@ -511,3 +511,30 @@ def test_geometry_cache_hits_with_a_non_contiguous_view_matrix(C, dev):
     assert torch.equal(ref["color"], c1) and torch.equal(ref["radii"], radii2)
     R3, *_ = C.rasterize_gaussians(*args)
     assert C.geometry_cache_hits() == h0 + 1                    # entry was released when the backward started
+
+
+def test_async_forward_capacity_overflow_is_retried(C, dev):
+    """The sync-free forward runs on buffers sized from the previous call's counts.  When the scene outgrows them the
+    device raises an overflow flag (no out-of-bounds access: binning and composite become no-ops) and the host repeats
+    binning + composite with exactly sized buffers: results are identical to a first (two-phase) call."""
+    scene = synthetic.make_scene(P=60_000, W=480, H=320, sh_degree=None, seed=52)
+    d = synthetic.to_device(scene, dev)
+    C.set_geometry_cache(False)
+    C._size_hint.clear()
+    first = run_ours(C, d)                                   # no hint: gsr_forward_geometry + gsr_forward_render
+    key = next(iter(C._size_hint))
+    assert C._size_hint[key][0] >= first["R"]
+    second = run_ours(C, d)                                  # hint: gsr_forward_async
+    for k in ("point_list", "ranges", "n_contrib"):
+        assert torch.equal(first["views"][k], second["views"][k]), k
+    assert torch.equal(first["color"], second["color"]) and first["R"] == second["R"]
+    n0 = C._counters.get("overflow_retries", 0)
+    for caps in ((first["R"] // 2, 10**8), (10**8, 100), (0, 0), (1, 1)):
+        C._size_hint[key] = caps                             # instance capacity / coarse capacity too small
+        o = run_ours(C, d)
+        assert torch.equal(o["color"], first["color"]) and o["R"] == first["R"]
+        assert torch.equal(o["views"]["point_list"], first["views"]["point_list"])
+        for n in ("dL_dmeans3D", "dL_dcolors"):
+            assert rel_err(o["grads"][n].cpu().numpy(), first["grads"][n].cpu().numpy()) < 1e-5
+    assert C._counters.get("overflow_retries", 0) == n0 + 4
+    C.set_geometry_cache(True)

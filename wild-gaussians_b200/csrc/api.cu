@@ -206,6 +206,83 @@ int gsr_binning_sizes(int P, int W, int H, int num_rendered, int num_coarse, siz
     return 0;
 }
 
+// projection, depth ordering (compacting away everything that is culled or outside the band) and coarse-item offsets;
+// leaves R (exact), N1 and the number of sorted Gaussians in g.counters.  No host synchronisation.
+static int geometry_stage(const GsrForwardArgs* a, const GeomState& g, int ty0, int ty1, cudaStream_t s) {
+    const bool dbg = a->debug != 0;
+    GSR_CUDA(cudaMemsetAsync(g.counters, 0, 8 * sizeof(int32_t), s));
+    prof_begin(ST_PREPROCESS_FWD, s);
+    int rc = launch_preprocess_fwd(*a, g, ty0, ty1, s);
+    if (rc) return rc;
+    GSR_STAGE(s, dbg, "preprocess_fwd_kernel");
+    prof_end(ST_PREPROCESS_FWD, s);
+
+    // front-to-back order of the Gaussians: stable sort on the depth bits (all 32, u32 compare like the reference's
+    // key, rasterizer_impl.cu:104).  The first pass drops the Gaussians that are culled or do not meet this rank's
+    // tile-row band (key = RADIX_DROP_KEY): the later passes, the scan and the emission only see the survivors, whose
+    // number stays on the device (counters[5]).
+    prof_begin(ST_DEPTH_SORT, s);
+    // the last pass also gathers cells_touched and the tile rectangles into depth order (own arrays: the pass
+    // reads key_b / val_b and writes key_a / val_a, nothing may alias those while it runs)
+    RadixAux aux;
+    aux.in32 = g.cells_touched;
+    aux.out32 = g.cells_sorted;
+    aux.in64 = reinterpret_cast<const uint2*>(g.rect);
+    aux.out64 = reinterpret_cast<uint2*>(g.rect_sorted);
+    uint32_t* n_sorted = reinterpret_cast<uint32_t*>(g.counters + 5);
+    rc = radix_sort_pairs(g.key_a, g.val_a, g.key_b, g.val_b, (size_t)a->P, 0, 32, g.radix_tmp, s, dbg, &aux, nullptr, n_sorted);
+    if (rc) return rc;
+    prof_end(ST_DEPTH_SORT, s);
+
+    // coarse-item offsets in depth order; the total (number of coarse items) goes to counters[4]
+    prof_begin(ST_OFFSET_SCAN, s);
+    rc = scan_gathered(g.cells_sorted, nullptr, g.offsets, (size_t)a->P, g.radix_tmp + radix_tmp_elems((size_t)a->P), s, n_sorted,
+                       reinterpret_cast<uint32_t*>(g.counters + 4));
+    if (rc) return rc;
+    GSR_STAGE(s, dbg, "scan_gathered");
+    prof_end(ST_OFFSET_SCAN, s);
+    return 0;
+}
+
+// synchronising read-back of the counters through a small pinned buffer (a pageable destination makes the copies
+// synchronous staging copies); one buffer per host thread, never freed
+static int read_counters(const GeomState& g, cudaStream_t s, int32_t out[8]) {
+    static thread_local int32_t* h_counts = nullptr;
+    if (!h_counts) GSR_CUDA(cudaHostAlloc((void**)&h_counts, 8 * sizeof(int32_t), cudaHostAllocDefault));
+    GSR_CUDA(cudaMemcpyAsync(h_counts, g.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    GSR_CUDA(cudaStreamSynchronize(s));
+    memcpy(out, h_counts, 8 * sizeof(int32_t));
+    return 0;
+}
+
+static int counts_of(const int32_t c[8], int* num_rendered, int* num_coarse) {
+    if (c[0] != 0) {
+        set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
+        return GSR_E_PREFILTERED;
+    }
+    unsigned long long R = 0;
+    memcpy(&R, &c[2], sizeof(R));
+    const uint32_t N1 = (uint32_t)c[4];
+    if (R > 0x7FFFFFFFull || N1 > 0x7FFFFFFFu) { set_error("instance count %llu overflows int", R); return GSR_E_OVERFLOW; }
+    *num_rendered = (int)R;
+    *num_coarse = (int)N1;
+    return 0;
+}
+
+static int binning_and_render(const GsrForwardArgs* a, const GeomState& g, const ImgState& im, const BinState& b,
+                              const BinScratch& bs, size_t R_cap, size_t N1_cap, int ty0, int ty1, cudaStream_t s) {
+    const bool dbg = a->debug != 0;
+    int rc = run_tile_binning(g, a->P, a->W, a->H, R_cap, N1_cap, bs, b.point_list, im.ranges, s, dbg);
+    if (rc) return rc;
+    const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
+    prof_begin(ST_RENDER_FWD, s);
+    rc = launch_render_fwd(*a, g, b, im, colors, ty0, ty1, s);
+    if (rc) return rc;
+    GSR_STAGE(s, dbg, "render_fwd_kernel");
+    prof_end(ST_RENDER_FWD, s);
+    return 0;
+}
+
 int gsr_forward_geometry(const GsrForwardArgs* a, void* geom_buffer, void* img_buffer, void* stream, int* num_rendered,
                          int* num_coarse) {
     (void)img_buffer;
@@ -217,59 +294,16 @@ int gsr_forward_geometry(const GsrForwardArgs* a, void* geom_buffer, void* img_b
     if (a->P == 0) return 0;
     if (!geom_buffer) { set_error("geom_buffer is NULL"); return GSR_E_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
-    const bool dbg = a->debug != 0;
     GeomState g;
     carve_geom((char*)geom_buffer, a->P, a->M, &g);
     int ty0, ty1;
     shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
-
-    GSR_CUDA(cudaMemsetAsync(g.counters, 0, 8 * sizeof(int32_t), s));
-    prof_begin(ST_PREPROCESS_FWD, s);
-    rc = launch_preprocess_fwd(*a, g, ty0, ty1, s);
+    rc = geometry_stage(a, g, ty0, ty1, s);
     if (rc) return rc;
-    GSR_STAGE(s, dbg, "preprocess_fwd_kernel");
-    prof_end(ST_PREPROCESS_FWD, s);
-
-    // front-to-back order of the Gaussians: stable sort on the depth bits (all 32, u32 compare
-    // like the reference's key, rasterizer_impl.cu:104); culled ones carry 0xFFFFFFFF.
-    prof_begin(ST_DEPTH_SORT, s);
-    // the last pass also gathers cells_touched and the tile rectangles into depth order (own arrays: the pass
-    // reads key_b / val_b and writes key_a / val_a, nothing may alias those while it runs)
-    RadixAux aux;
-    aux.in32 = g.cells_touched;
-    aux.out32 = g.cells_sorted;
-    aux.in64 = reinterpret_cast<const uint2*>(g.rect);
-    aux.out64 = reinterpret_cast<uint2*>(g.rect_sorted);
-    rc = radix_sort_pairs(g.key_a, g.val_a, g.key_b, g.val_b, (size_t)a->P, 0, 32, g.radix_tmp, s, dbg, &aux);
+    int32_t c[8];
+    rc = read_counters(g, s, c);
     if (rc) return rc;
-    prof_end(ST_DEPTH_SORT, s);
-
-    // coarse-item offsets in depth order; offsets[P] = number of coarse items
-    prof_begin(ST_OFFSET_SCAN, s);
-    rc = scan_gathered(g.cells_sorted, nullptr, g.offsets, (size_t)a->P, g.radix_tmp + radix_tmp_elems((size_t)a->P), s);
-    if (rc) return rc;
-    GSR_STAGE(s, dbg, "scan_gathered");
-    prof_end(ST_OFFSET_SCAN, s);
-
-    // read-back of the counts through a small pinned buffer (a pageable destination makes the copies synchronous
-    // staging copies); one buffer per host thread, never freed
-    static thread_local int32_t* h_counts = nullptr;
-    if (!h_counts) GSR_CUDA(cudaHostAlloc((void**)&h_counts, 16 * sizeof(int32_t), cudaHostAllocDefault));
-    GSR_CUDA(cudaMemcpyAsync(h_counts + 8, g.offsets + a->P, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    GSR_CUDA(cudaMemcpyAsync(h_counts, g.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    GSR_CUDA(cudaStreamSynchronize(s));
-    const int32_t* counters = h_counts;
-    const uint32_t N1 = (uint32_t)h_counts[8];
-    if (counters[0] != 0) {
-        set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
-        return GSR_E_PREFILTERED;
-    }
-    unsigned long long R = 0;
-    memcpy(&R, &counters[2], sizeof(R));
-    if (R > 0x7FFFFFFFull || N1 > 0x7FFFFFFFu) { set_error("instance count %llu overflows int", R); return GSR_E_OVERFLOW; }
-    *num_rendered = (int)R;
-    *num_coarse = (int)N1;
-    return 0;
+    return counts_of(c, num_rendered, num_coarse);
 }
 
 int gsr_forward_render(const GsrForwardArgs* a, void* geom_buffer, void* img_buffer, void* binning_buffer, void* scratch,
@@ -281,30 +315,56 @@ int gsr_forward_render(const GsrForwardArgs* a, void* geom_buffer, void* img_buf
         set_error("a buffer is NULL");
         return GSR_E_INVALID;
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    const bool dbg = a->debug != 0;
     GeomState g;
     ImgState im;
     BinState b;
     BinScratch bs;
     carve_geom((char*)geom_buffer, a->P, a->M, &g);
     carve_img((char*)img_buffer, a->W, a->H, &im);
-    const size_t R = (size_t)num_rendered;
-    carve_bin((char*)binning_buffer, R, &b);
+    carve_bin((char*)binning_buffer, (size_t)num_rendered, &b);
     carve_bin_scratch((char*)scratch, (size_t)num_coarse, a->W, a->H, &bs);
     int ty0, ty1;
     shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
+    return binning_and_render(a, g, im, b, bs, (size_t)num_rendered, (size_t)num_coarse, ty0, ty1, (cudaStream_t)stream);
+}
 
-    rc = run_tile_binning(g, a->P, a->W, a->H, R, (size_t)num_coarse, bs, b.point_list, im.ranges, s, dbg);
+int gsr_forward_async(const GsrForwardArgs* a, void* geom_buffer, void* img_buffer, void* binning_buffer,
+                      int rendered_capacity, void* scratch, int coarse_capacity, void* stream) {
+    int rc = check_fwd_args(a);
     if (rc) return rc;
+    if (a->P == 0) return 0;
+    if (!geom_buffer || !img_buffer || rendered_capacity < 0 || coarse_capacity < 0 ||
+        ((rendered_capacity > 0 && coarse_capacity > 0) && (!binning_buffer || !scratch))) {
+        set_error("a buffer is NULL or a capacity is negative");
+        return GSR_E_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    GeomState g;
+    ImgState im;
+    BinState b;
+    BinScratch bs;
+    carve_geom((char*)geom_buffer, a->P, a->M, &g);
+    carve_img((char*)img_buffer, a->W, a->H, &im);
+    carve_bin((char*)binning_buffer, (size_t)rendered_capacity, &b);
+    carve_bin_scratch((char*)scratch, (size_t)coarse_capacity, a->W, a->H, &bs);
+    int ty0, ty1;
+    shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
+    rc = geometry_stage(a, g, ty0, ty1, s);
+    if (rc) return rc;
+    return binning_and_render(a, g, im, b, bs, (size_t)rendered_capacity, (size_t)coarse_capacity, ty0, ty1, s);
+}
 
-    const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
-    prof_begin(ST_RENDER_FWD, s);
-    rc = launch_render_fwd(*a, g, b, im, colors, ty0, ty1, s);
+int gsr_forward_status(const void* geom_buffer, int P, int M, void* stream, int* num_rendered, int* num_coarse, int* overflow) {
+    if (!geom_buffer || !num_rendered || !num_coarse || !overflow) { set_error("NULL argument"); return GSR_E_INVALID; }
+    *num_rendered = *num_coarse = *overflow = 0;
+    if (P == 0) return 0;
+    GeomState g;
+    carve_geom((char*)geom_buffer, P, M, &g);
+    int32_t c[8];
+    int rc = read_counters(g, (cudaStream_t)stream, c);
     if (rc) return rc;
-    GSR_STAGE(s, dbg, "render_fwd_kernel");
-    prof_end(ST_RENDER_FWD, s);
-    return 0;
+    *overflow = c[6];
+    return counts_of(c, num_rendered, num_coarse);
 }
 
 int gsr_forward(const GsrForwardArgs* a, gsr_alloc_fn alloc, void* ctx, void* stream, int* num_rendered) {
@@ -499,15 +559,12 @@ int gsr_get_stats(const void* geom_buffer, int P, int M, void* stream, GsrStats*
     GeomState g;
     carve_geom((char*)geom_buffer, P, M, &g);
     int32_t c[8];
-    cudaStream_t s = (cudaStream_t)stream;
-    uint32_t n1 = 0;
-    GSR_CUDA(cudaMemcpyAsync(c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
-    GSR_CUDA(cudaMemcpyAsync(&n1, g.offsets + P, sizeof(n1), cudaMemcpyDeviceToHost, s));
-    GSR_CUDA(cudaStreamSynchronize(s));
+    int rc = read_counters(g, (cudaStream_t)stream, c);
+    if (rc) return rc;
     out->num_visible = c[1];
     out->num_rendered = c[2];   // low word of the 64-bit instance counter
     out->num_tiles = 0;
-    out->num_coarse = (int)n1;
+    out->num_coarse = c[4];
     return 0;
 }
 

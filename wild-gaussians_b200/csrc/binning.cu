@@ -30,12 +30,27 @@ namespace gsr {
 
 // ---- level 1: coarse items ------------------------------------------------------------------------
 // key = cell id (low 16 bits) | x0 << 16 | y0 << 20 | x1 << 24 | y1 << 28, rectangle local to the cell
-__global__ void __launch_bounds__(256) emit_cells_kernel(int P, int cells_x, const uint32_t* __restrict__ order,
+// counters (GeomState::counters): [2..3] R = exact instance count of the band (u64, preprocess), [4] N1 = coarse
+// items (scan total), [5] number of depth-sorted Gaussians, [6] overflow flags, [7] N1 if everything fits the supplied
+// buffers, else 0 -- the item count every later binning kernel works with, so that an overflow turns the rest of
+// the forward into a harmless no-op (empty tile ranges) instead of writing out of bounds; the host re-runs with
+// exact sizes when it sees the flag.
+__global__ void __launch_bounds__(256) emit_cells_kernel(int cells_x, const uint32_t* __restrict__ order,
                                                          const uint32_t* __restrict__ offsets,
                                                          const TileRect* __restrict__ rect,
-                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // position in depth order
-    if (i >= P) return;
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                         int32_t* __restrict__ counters, uint32_t n1_cap,
+                                                         unsigned long long r_cap) {
+    const uint32_t n1 = (uint32_t)counters[4];
+    const unsigned long long R = *reinterpret_cast<const unsigned long long*>(counters + 2);
+    const bool fits = n1 <= n1_cap && R <= r_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counters[7] = fits ? (int32_t)n1 : 0;
+        if (!fits) counters[6] = (n1 > n1_cap ? 1 : 0) | (R > r_cap ? 2 : 0);
+    }
+    if (!fits) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;   // position in depth order
+    if (i >= (uint32_t)counters[5]) return;
     const uint32_t g = order[i];
     const TileRect r = rect[i];      // rectangles arrive in depth order (gathered by the last sort pass)
     if (r.x1 <= r.x0 || r.y1 <= r.y0) return;
@@ -54,9 +69,10 @@ __global__ void __launch_bounds__(256) emit_cells_kernel(int P, int cells_x, con
 }
 
 // cell_range[c] = [first, end) of cell c in the sorted coarse list; empty cells keep (0, 0)
-__global__ void __launch_bounds__(256) cell_bounds_kernel(const uint32_t* __restrict__ keys, uint32_t n1,
+__global__ void __launch_bounds__(256) cell_bounds_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ n1_dev,
                                                           uint2* __restrict__ cell_range) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n1 = (uint32_t)*n1_dev;
     if (i >= n1) return;
     const uint32_t c = keys[i] & 0xFFFFu;
     if (i == 0) {
@@ -427,14 +443,17 @@ __global__ void __launch_bounds__(SQ_WARPS * 32) cell_scatter_staged_kernel(
 }
 
 // ---- orchestration -----------------------------------------------------------------------------------
-int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R, size_t N1, const BinScratch& bs,
+int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R_cap, size_t N1_cap, const BinScratch& bs,
                      uint32_t* point_list, uint2* ranges, cudaStream_t s, bool debug) {
     const int gx = tiles_x(W), gy = tiles_y(H);
     const int cells_x = (gx + CELL - 1) / CELL, cells_y = (gy + CELL - 1) / CELL;
     const uint32_t num_cells = (uint32_t)(cells_x * cells_y);
     const int num_tiles = gx * gy;
-    if (N1 == 0 || R == 0) {
+    if (N1_cap == 0 || R_cap == 0) {
+        // nothing can be binned: empty ranges; a non-empty scene then shows up as an overflow (flags set by this kernel)
         GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s));
+        emit_cells_kernel<<<1, 32, 0, s>>>(cells_x, g.order, g.offsets, g.rect_sorted, nullptr, nullptr, g.counters, 0u, 0ull);
+        count_launches(1);
         return 0;
     }
     // level 1: emit + stable sort by cell id; the sorted result must land in (key_b, val_b)
@@ -446,12 +465,15 @@ int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R, size_t N
     uint32_t* va = even ? bs.val_b : bs.val_a;
     uint32_t* kb = even ? bs.key_a : bs.key_b;
     uint32_t* vb = even ? bs.val_a : bs.val_b;
-    emit_cells_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, cells_x, g.order, g.offsets, g.rect_sorted, ka, va);
+    emit_cells_kernel<<<(P + 255) / 256, 256, 0, s>>>(cells_x, g.order, g.offsets, g.rect_sorted, ka, va, g.counters,
+                                                      (uint32_t)N1_cap, (unsigned long long)R_cap);
     count_launches(1);
     GSR_STAGE(s, debug, "emit_cells_kernel");
     prof_end(ST_EMIT_CELLS, s);
     prof_begin(ST_CELL_SORT, s);
-    int rc = radix_sort_pairs(ka, va, kb, vb, N1, 0, cell_bits, bs.radix_tmp, s, debug);
+    const uint32_t* n1_dev = reinterpret_cast<const uint32_t*>(g.counters + 7);
+    const size_t N1 = N1_cap;
+    int rc = radix_sort_pairs(ka, va, kb, vb, N1, 0, cell_bits, bs.radix_tmp, s, debug, nullptr, n1_dev);
     if (rc) return rc;
     const uint32_t* keys = bs.key_b;
     const uint32_t* vals = bs.val_b;
@@ -466,7 +488,7 @@ int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R, size_t N
         count_launches(1);
     } else {
         GSR_CUDA(cudaMemsetAsync(bs.cell_range, 0, (size_t)num_cells * sizeof(uint2), s));
-        cell_bounds_kernel<<<(unsigned)((N1 + 255) / 256), 256, 0, s>>>(keys, (uint32_t)N1, bs.cell_range);
+        cell_bounds_kernel<<<(unsigned)((N1 + 255) / 256), 256, 0, s>>>(keys, g.counters + 7, bs.cell_range);
         count_launches(1);
         build_units_kernel<<<1, 1024, 0, s>>>(bs.cell_range, num_cells, bs.unit_base, nullptr);
         count_launches(1);

@@ -120,13 +120,17 @@ struct RadixAux {
     const uint2* in64;
     uint2* out64;
 };
-int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, size_t n,
-                     int begin_bit, int end_bit, uint32_t* tmp, cudaStream_t s, bool debug, const RadixAux* aux = nullptr);
+// n_cap sizes the grids; with n_dev the item count is min(*n_dev, n_cap) (device side).  With n_compact the first pass
+// drops the items whose key is RADIX_DROP_KEY and stores the number of remaining items in *n_compact.
+constexpr uint32_t RADIX_DROP_KEY = 0xFFFFFFFFu;
+int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, size_t n_cap,
+                     int begin_bit, int end_bit, uint32_t* tmp, cudaStream_t s, bool debug, const RadixAux* aux = nullptr,
+                     const uint32_t* n_dev = nullptr, uint32_t* n_compact = nullptr);
 // digit totals (RADIX entries) left in `tmp` by the most recent pass of radix_sort_pairs over n items
 const uint32_t* radix_pass_totals(const uint32_t* tmp, size_t n);
 // exclusive scan of gathered counts: out[i] = sum_{j<i} counts[perm[j]], out[n] = total
-int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, size_t n,
-                  uint32_t* tmp, cudaStream_t s);
+int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, size_t n_cap,
+                  uint32_t* tmp, cudaStream_t s, const uint32_t* n_dev = nullptr, uint32_t* total_out = nullptr);
 size_t scan_tmp_elems(size_t n);
 
 // in-place exclusive scan along each row of a [rows][cols] u32 matrix; row sums -> total[rows]

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
     // defaults for Gaussians that are not rendered
     int out_radius = 0;
     uint32_t out_tiles = 0, out_cells = 0;
-    uint32_t out_key = 0xFFFFFFFFu;   // culled Gaussians sort to the back
+    uint32_t out_key = RADIX_DROP_KEY;   // culled Gaussians (and those outside the tile-row band) are dropped by the depth sort
     TileRect out_rect = {0, 0, 0, 0};
     bool visible = false;
 
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const __grid_consta
         out_tiles = rows * (rx1 - rx0);
         out_rect = {(uint16_t)rx0, (uint16_t)(rows ? cy0 : 0u), (uint16_t)rx1, (uint16_t)(rows ? cy1 : 0u)};
         if (rows) out_cells = ((rx1 - 1) / CELL - rx0 / CELL + 1) * ((cy1 - 1) / CELL - cy0 / CELL + 1);
-        out_key = __float_as_uint(p_view.z);
+        if (rows) out_key = __float_as_uint(p_view.z);    // view-space z > 0.2: never equals the drop key
 
         // Screen-space half extents of the region where this Gaussian can reach alpha >= 1/255
         // (axis-aligned box of the ellipse d^T Sigma^-1 d <= 2 ln(255 o)), inflated by a safety margin

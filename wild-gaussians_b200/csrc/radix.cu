@@ -37,12 +37,28 @@ size_t radix_tmp_elems(size_t n) {
     return (size_t)RADIX * radix_ctas(n) + RADIX + 64;
 }
 
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int shift,
+// The item count is min(*n_dev, n_cap) when n_dev != NULL (the grid is sized for n_cap; CTAs beyond the count publish
+// zero histogram columns).  DROP: keys equal to RADIX_DROP_KEY are not part of the sort at all (neither counted nor
+// scattered): the first pass of the depth sort compacts away the Gaussians that are culled / outside the tile-row band.
+__device__ __forceinline__ size_t radix_count(size_t n_cap, const uint32_t* __restrict__ n_dev) {
+    if (n_dev == nullptr) return n_cap;
+    const size_t n = *n_dev;
+    return n < n_cap ? n : n_cap;
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* __restrict__ keys, size_t n_cap,
+                                                                const uint32_t* __restrict__ n_dev, int shift,
                                                                 uint32_t mask, uint32_t* __restrict__ hist, uint32_t ctas) {
     __shared__ uint32_t s_hist[RADIX];
+    const size_t n = radix_count(n_cap, n_dev);
+    const size_t base = (size_t)blockIdx.x * RS_CHUNK;
+    if (base >= n) {
+        for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) hist[(size_t)i * ctas + blockIdx.x] = 0;
+        return;
+    }
     for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) s_hist[i] = 0;
     __syncthreads();
-    const size_t base = (size_t)blockIdx.x * RS_CHUNK;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // plain shared-memory atomics: with 256 bins the lanes of a warp rarely collide on random digits, and a
     // warp whose lanes all hit one bin (constant high digits) is serialised by the hardware in ~32 cycles.
@@ -57,7 +73,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t* 
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const size_t i = base + (size_t)warp * RS_WARP_ITEMS + r * 32 + lane;
-        if (i < n) atomicAdd(&s_hist[(k[r] >> shift) & mask], 1u);
+        if (i < n && !(DROP && k[r] == RADIX_DROP_KEY)) atomicAdd(&s_hist[(k[r] >> shift) & mask], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < RADIX; i += RS_THREADS) hist[(size_t)i * ctas + blockIdx.x] = s_hist[i];
@@ -103,19 +119,35 @@ __global__ void __launch_bounds__(1024) radix_rowscan_kernel(uint32_t* __restric
     if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
 }
 
-template <bool WRITE_KEYS, bool AUX>
+template <bool DROP, bool AUX>
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                    const uint32_t* __restrict__ vals_in,
                                                                    uint32_t* __restrict__ keys_out,
-                                                                   uint32_t* __restrict__ vals_out, size_t n, int shift,
+                                                                   uint32_t* __restrict__ vals_out, size_t n_cap,
+                                                                   const uint32_t* __restrict__ n_dev, int shift,
                                                                    uint32_t mask, const uint32_t* __restrict__ hist,
                                                                    const uint32_t* __restrict__ total, uint32_t ctas,
-                                                                   const RadixAux aux) {
+                                                                   const RadixAux aux, uint32_t* __restrict__ n_out) {
     __shared__ uint32_t s_cnt[RS_WARPS][RADIX];   // per-warp digit counters, later global bases
     __shared__ uint32_t s_digit_base[RADIX];
     __shared__ uint32_t s_key[RS_CHUNK];
     __shared__ uint32_t s_val[RS_CHUNK];
+    __shared__ uint32_t s_kept;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t n = radix_count(n_cap, n_dev);
+    // number of items that take part in the sort (all digit totals): the next passes' item count
+    if (n_out != nullptr && blockIdx.x == 0) {
+        __shared__ uint32_t s_t[RS_WARPS];
+        const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, total[threadIdx.x]);
+        if (lane == 0) s_t[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t sum = 0;
+            for (int w = 0; w < RS_WARPS; ++w) sum += s_t[w];
+            *n_out = sum;
+        }
+    }
+    if ((size_t)blockIdx.x * RS_CHUNK >= n) return;
     for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
 
     // exclusive scan of the digit totals (256 values, one per thread)
@@ -144,13 +176,13 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
     for (int r = 0; r < RS_ITEMS; ++r) {
         const size_t i = base + r * 32 + lane;
         const bool valid = i < n;
-        key[r] = valid ? keys_in[i] : 0u;
+        key[r] = valid ? keys_in[i] : RADIX_DROP_KEY;
         val[r] = valid ? vals_in[i] : 0u;
     }
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const size_t i = base + r * 32 + lane;
-        const bool valid = i < n;
+        const bool valid = i < n && !(DROP && key[r] == RADIX_DROP_KEY);
         const uint32_t d = valid ? ((key[r] >> shift) & mask) : 0u;
         // lanes holding the same digit: 8 ballots (one per digit bit) instead of __match_any_sync, whose cost
         // grows with the number of distinct digits in the warp
@@ -190,6 +222,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
         uint32_t off = 0;
         for (int w = 0; w < warp; ++w) off += s_w2[w];
         uint32_t loc = off + x - run;   // first chunk position of digit d
+        if (d == RADIX - 1) s_kept = off + x;   // items of this chunk that take part in the sort
         s_digit_base[d] -= loc;         // global position = chunk position + s_digit_base[d]  (mod 2^32)
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) { s_cnt[w][d] = loc; loc += c[w]; }
@@ -200,7 +233,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
         const size_t i = base + r * 32 + lane;
-        if (i < n) {
+        if (i < n && !(DROP && key[r] == RADIX_DROP_KEY)) {
             const uint32_t d = (key[r] >> shift) & mask;
             const uint32_t li = s_cnt[warp][d] + rank[r];
             s_key[li] = key[r];
@@ -208,13 +241,12 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_
         }
     }
     __syncthreads();
-    const size_t cta_base = (size_t)blockIdx.x * RS_CHUNK;
-    const uint32_t cta_n = (uint32_t)min((size_t)RS_CHUNK, n - cta_base);
+    const uint32_t cta_n = s_kept;
 #pragma unroll 4
     for (uint32_t i = threadIdx.x; i < cta_n; i += RS_THREADS) {
         const uint32_t k = s_key[i];
         const uint32_t pos = i + s_digit_base[(k >> shift) & mask];
-        if (WRITE_KEYS) keys_out[pos] = k;
+        keys_out[pos] = k;
         const uint32_t v = s_val[i];
         vals_out[pos] = v;
         if (AUX) {
@@ -241,15 +273,19 @@ int radix_num_passes(int begin_bit, int end_bit) {
     return nbits <= 0 ? 0 : (nbits + RADIX_BITS - 1) / RADIX_BITS;
 }
 
-int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, size_t n, int begin_bit,
-                     int end_bit, uint32_t* tmp, cudaStream_t s, bool debug, const RadixAux* aux) {
+int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t* val_b, size_t n_cap, int begin_bit,
+                     int end_bit, uint32_t* tmp, cudaStream_t s, bool debug, const RadixAux* aux, const uint32_t* n_dev,
+                     uint32_t* n_compact) {
     // Stable sort on key bits [begin_bit, end_bit).  The input is (key_a, val_a); passes
     // ping-pong A -> B -> A ..., clobbering both.  With an even number of passes
     // (radix_num_passes) the result is in A, with an odd number in B; callers place their
     // buffers accordingly.
-    if (n == 0) return 0;
+    // n_cap sizes the grids; the item count is min(*n_dev, n_cap) when n_dev is given.  With n_compact != NULL the
+    // first pass drops the items whose key is RADIX_DROP_KEY and stores the number of remaining items in *n_compact,
+    // which is the item count of the following passes.
+    if (n_cap == 0) return 0;
     const int passes = radix_num_passes(begin_bit, end_bit);
-    const uint32_t ctas = (uint32_t)radix_ctas(n);
+    const uint32_t ctas = (uint32_t)radix_ctas(n_cap);
     uint32_t* hist = tmp;
     uint32_t* total = tmp + (size_t)RADIX * ctas;
     for (int pass = 0; pass < passes; ++pass) {
@@ -261,16 +297,21 @@ int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t
         const uint32_t* vin = a_to_b ? val_a : val_b;
         uint32_t* kout = a_to_b ? key_b : key_a;
         uint32_t* vout = a_to_b ? val_b : val_a;
-        radix_hist_kernel<<<ctas, RS_THREADS, 0, s>>>(kin, n, shift, mask, hist, ctas);
+        const bool drop = n_compact != nullptr && pass == 0;
+        const uint32_t* nd = (n_compact != nullptr && pass > 0) ? n_compact : n_dev;
+        if (drop) radix_hist_kernel<true><<<ctas, RS_THREADS, 0, s>>>(kin, n_cap, nd, shift, mask, hist, ctas);
+        else radix_hist_kernel<false><<<ctas, RS_THREADS, 0, s>>>(kin, n_cap, nd, shift, mask, hist, ctas);
         count_launches(1);
         GSR_STAGE(s, debug, "radix_hist_kernel");
         radix_rowscan_kernel<<<RADIX, 1024, 0, s>>>(hist, ctas, total);
         count_launches(1);
         GSR_STAGE(s, debug, "radix_rowscan_kernel");
-        if (aux && pass == passes - 1)
-            radix_scatter_kernel<true, true><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, total, ctas, *aux);
-        else
-            radix_scatter_kernel<true, false><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, mask, hist, total, ctas, RadixAux{});
+        const bool with_aux = aux && pass == passes - 1;
+        const RadixAux ax = with_aux ? *aux : RadixAux{};
+        if (drop && with_aux) radix_scatter_kernel<true, true><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n_cap, nd, shift, mask, hist, total, ctas, ax, n_compact);
+        else if (drop) radix_scatter_kernel<true, false><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n_cap, nd, shift, mask, hist, total, ctas, ax, n_compact);
+        else if (with_aux) radix_scatter_kernel<false, true><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n_cap, nd, shift, mask, hist, total, ctas, ax, nullptr);
+        else radix_scatter_kernel<false, false><<<ctas, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n_cap, nd, shift, mask, hist, total, ctas, ax, nullptr);
         count_launches(1);
         GSR_STAGE(s, debug, "radix_scatter_kernel");
     }
@@ -309,10 +350,16 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
 }
 
 __global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ counts,
-                                                                 const uint32_t* __restrict__ perm, size_t n,
+                                                                 const uint32_t* __restrict__ perm, size_t n_cap,
+                                                                 const uint32_t* __restrict__ n_dev,
                                                                  uint32_t* __restrict__ partial) {
     __shared__ uint32_t s_warp[SC_THREADS / 32];
+    const size_t n = radix_count(n_cap, n_dev);
     const size_t base = (size_t)blockIdx.x * SC_CHUNK;
+    if (base >= n) {
+        if (threadIdx.x == 0) partial[blockIdx.x] = 0;
+        return;
+    }
     uint32_t sum = 0;
 #pragma unroll
     for (int k = 0; k < SC_ITEMS; ++k) {
@@ -363,10 +410,17 @@ __global__ void __launch_bounds__(1024) scan_partials_kernel(uint32_t* __restric
 }
 
 __global__ void __launch_bounds__(SC_THREADS) scan_apply_kernel(const uint32_t* __restrict__ counts,
-                                                                const uint32_t* __restrict__ perm, size_t n,
+                                                                const uint32_t* __restrict__ perm, size_t n_cap,
+                                                                const uint32_t* __restrict__ n_dev,
                                                                 const uint32_t* __restrict__ partial, uint32_t m,
-                                                                uint32_t* __restrict__ out) {
+                                                                uint32_t* __restrict__ out, uint32_t* __restrict__ total_out) {
     __shared__ uint32_t s_warp[SC_THREADS / 32];
+    const size_t n = radix_count(n_cap, n_dev);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out[n] = partial[m];
+        if (total_out) *total_out = partial[m];
+    }
+    if ((size_t)blockIdx.x * SC_CHUNK >= n) return;
     // blocked arrangement: thread t owns items [t*SC_ITEMS, (t+1)*SC_ITEMS) of the chunk
     const size_t base = (size_t)blockIdx.x * SC_CHUNK + (size_t)threadIdx.x * SC_ITEMS;
     uint32_t v[SC_ITEMS];
@@ -385,20 +439,22 @@ __global__ void __launch_bounds__(SC_THREADS) scan_apply_kernel(const uint32_t* 
         if (i < n) out[i] = off;
         off += v[k];
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = partial[m];
 }
 
-int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, size_t n, uint32_t* tmp, cudaStream_t s) {
-    if (n == 0) {
+// out[i] = sum_{j<i} counts[perm[j]] for i < n, out[n] = total (also stored in *total_out); n = min(*n_dev, n_cap)
+int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, size_t n_cap, uint32_t* tmp, cudaStream_t s,
+                  const uint32_t* n_dev, uint32_t* total_out) {
+    if (n_cap == 0) {
         GSR_CUDA(cudaMemsetAsync(out, 0, 4, s));
+        if (total_out) GSR_CUDA(cudaMemsetAsync(total_out, 0, 4, s));
         return 0;
     }
-    const uint32_t m = (uint32_t)((n + SC_CHUNK - 1) / SC_CHUNK);
-    scan_reduce_kernel<<<m, SC_THREADS, 0, s>>>(counts, perm, n, tmp);
+    const uint32_t m = (uint32_t)((n_cap + SC_CHUNK - 1) / SC_CHUNK);
+    scan_reduce_kernel<<<m, SC_THREADS, 0, s>>>(counts, perm, n_cap, n_dev, tmp);
     count_launches(1);
     scan_partials_kernel<<<1, 1024, 0, s>>>(tmp, m);
     count_launches(1);
-    scan_apply_kernel<<<m, SC_THREADS, 0, s>>>(counts, perm, n, tmp, m, out);
+    scan_apply_kernel<<<m, SC_THREADS, 0, s>>>(counts, perm, n_cap, n_dev, tmp, m, out, total_out);
     count_launches(1);
     GSR_CUDA(cudaGetLastError());
     return 0;

@@ -76,6 +76,8 @@ def _load():
     lib.gsr_forward_geometry.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int)]
     lib.gsr_binning_sizes.argtypes = [c_int, c_int, c_int, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]
     lib.gsr_forward_render.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.gsr_forward_async.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]
+    lib.gsr_forward_status.argtypes = [c_void_p, c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]
     lib.gsr_forward_recolor.argtypes = [POINTER(GsrForwardArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsr_backward_scratch_bytes.argtypes = [c_int]
     lib.gsr_backward_scratch_bytes.restype = c_size_t
@@ -105,7 +107,7 @@ def _load():
     lib.gsr_profile_read.argtypes = [POINTER(c_float), c_int]
     lib.gsr_launch_count.restype = ctypes.c_ulonglong
     for name in ("gsr_forward_sizes", "gsr_forward_geometry", "gsr_binning_sizes", "gsr_forward_render",
-                 "gsr_forward_recolor", "gsr_backward", "gsr_backward_partials", "gsr_backward_finalize",
+                 "gsr_forward_recolor", "gsr_forward_async", "gsr_forward_status", "gsr_backward", "gsr_backward_partials", "gsr_backward_finalize",
                  "gsr_backward_partials_peers",
                  "gsr_mark_visible", "gsr_img_views", "gsr_binning_views",
                  "gsr_geom_views", "gsr_get_stats"):
@@ -139,7 +141,9 @@ def get_tile_row_shard():
 # Modifying a tensor behind autograd's back (``x.data.add_(...)``, a raw kernel writing through data_ptr) does not
 # bump the version: call clear_geometry_cache() after such writes or set GSR_GEOM_CACHE=0.  The entry is dropped when
 # a backward pass starts (no further forward on this geometry can follow before the parameters change).
-_size_hint: dict = {}      # (P, W, H, shard) -> bytes of the binning / scratch buffers of the previous call
+_size_hint: dict = {}      # (P, W, H, shard) -> (instance capacity, coarse-item capacity) for the next call
+_counters: dict = {}       # bookkeeping: "overflow_retries"
+_ASYNC_FORWARD = os.environ.get("GSR_ASYNC_FORWARD", "1") != "0"
 _GEOM_CACHE_ON = os.environ.get("GSR_GEOM_CACHE", "1") != "0"
 _geom_cache: dict = {}
 
@@ -291,28 +295,42 @@ def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scale
         a.radii = radii.data_ptr()
         geom = torch.empty((gb.value,), **byte)
         img = torch.empty((ib.value,), **byte)
-        # The instance counts are known only after a device->host read-back inside gsr_forward_geometry.  To keep
-        # the GPU idle gap behind that synchronisation short, the two count-sized buffers are allocated beforehand
-        # from the sizes of the previous call with the same shape (training re-renders nearly the same scene) and
-        # re-allocated only if they turn out too small.
+        # Instance counts.  The reference blocks on them in the middle of its forward (rasterizer_impl.cu:283-284) and
+        # so does the two-phase protocol gsr_forward_geometry / gsr_forward_render.  When a previous call with the same
+        # shape left a capacity hint (training re-renders nearly the same scene), the whole forward is enqueued at once
+        # on buffers sized for that capacity (gsr_forward_async: no synchronisation, actual counts stay on the device)
+        # and the counts are read back once, at the END, where the caller waits for the result anyway; the GPU never
+        # idles in the middle of the forward.  If the scene outgrew the capacity the composite ran on empty tile lists:
+        # binning + composite are repeated with exactly sized buffers (the geometry stage is still valid).
         hint_key = (P, W, H, shard)
         hint = _size_hint.get(hint_key)
-        binning = scratch = None
-        if hint is not None:
-            binning = torch.empty((hint[0],), **byte)
-            scratch = torch.empty((hint[1],), **byte)
         R, N1 = c_int(0), c_int(0)
-        _check(_lib.gsr_forward_geometry(byref(a), geom.data_ptr(), img.data_ptr(), stream, byref(R), byref(N1)),
-               "gsr_forward_geometry")
         bb, sb = c_size_t(0), c_size_t(0)
-        _check(_lib.gsr_binning_sizes(P, W, H, R.value, N1.value, byref(bb), byref(sb)), "gsr_binning_sizes")
-        if binning is None or binning.numel() < bb.value:
-            binning = torch.empty((bb.value + bb.value // 16,), **byte)
-        if scratch is None or scratch.numel() < sb.value:
-            scratch = torch.empty((sb.value + sb.value // 16,), **byte)
-        _size_hint[hint_key] = (binning.numel(), scratch.numel())
-        _check(_lib.gsr_forward_render(byref(a), geom.data_ptr(), img.data_ptr(), binning.data_ptr(),
-                                       scratch.data_ptr(), R.value, N1.value, stream), "gsr_forward_render")
+        done = False
+        if hint is not None and _ASYNC_FORWARD:
+            _check(_lib.gsr_binning_sizes(P, W, H, hint[0], hint[1], byref(bb), byref(sb)), "gsr_binning_sizes")
+            binning = torch.empty((bb.value,), **byte)
+            scratch = torch.empty((sb.value,), **byte)
+            _check(_lib.gsr_forward_async(byref(a), geom.data_ptr(), img.data_ptr(), binning.data_ptr(), hint[0],
+                                          scratch.data_ptr(), hint[1], stream), "gsr_forward_async")
+            ovf = c_int(0)
+            _check(_lib.gsr_forward_status(geom.data_ptr(), P, M, stream, byref(R), byref(N1), byref(ovf)),
+                   "gsr_forward_status")
+            done = ovf.value == 0
+            if not done:
+                _counters["overflow_retries"] = _counters.get("overflow_retries", 0) + 1
+        else:
+            _check(_lib.gsr_forward_geometry(byref(a), geom.data_ptr(), img.data_ptr(), stream, byref(R), byref(N1)),
+                   "gsr_forward_geometry")
+        if not done:
+            _check(_lib.gsr_binning_sizes(P, W, H, R.value, N1.value, byref(bb), byref(sb)), "gsr_binning_sizes")
+            binning = torch.empty((bb.value,), **byte)
+            scratch = torch.empty((sb.value,), **byte)
+            _check(_lib.gsr_forward_render(byref(a), geom.data_ptr(), img.data_ptr(), binning.data_ptr(),
+                                           scratch.data_ptr(), R.value, N1.value, stream), "gsr_forward_render")
+        # capacity for the next call of this shape: the counts plus 1/8 (kept while the counts stay within it and above half)
+        if hint is None or R.value > hint[0] or N1.value > hint[1] or 2 * R.value < hint[0]:
+            _size_hint[hint_key] = (R.value + R.value // 8 + 4096, N1.value + N1.value // 8 + 4096)
         # `scratch` goes back to torch's stream-ordered caching allocator here: any later
         # allocation on this stream is ordered after the kernels that use it.
         del scratch
