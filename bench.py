@@ -189,6 +189,43 @@ def time_steps(step, steps, warmup, dev, world):
     return ms / steps
 
 
+def make_e2e_step_sharded(scene, dev, settings_cls, bands):
+    """Multi-GPU e2e: the host buffers hold the data once per rank (same bytes); rank r moves only the r-th 1/world of
+    every tensor over PCIe in either direction (parallel.upload_sharded / download_sharded), NVLink does the rest."""
+    import parallel
+    keys = [k for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp", "shs", "bg", "viewmatrix",
+                        "projmatrix", "campos", "subpixel_offset", "dL_dpix") if k in scene]
+    host = {k: scene[k].contiguous().pin_memory() for k in keys}
+    leaves_k = [k for k in ("means3D", "opacities", "scales", "rotations", "colors_precomp", "shs") if k in scene]
+    H, W, P = scene["image_height"], scene["image_width"], scene["means3D"].shape[0]
+    out_host = {"image": torch.empty((3, H, W)).pin_memory(), "means2D": torch.empty((P, 3)).pin_memory()}
+    for k in leaves_k:
+        out_host[k] = torch.empty_like(scene[k]).pin_memory()
+    h2d = sum(v.numel() * 4 for v in host.values())
+    d2h = sum(v.numel() * 4 for v in out_host.values())
+
+    def step():
+        d = {k: parallel.upload_sharded(v, dev) for k, v in host.items()}
+        st = settings_cls(image_height=H, image_width=W, tanfovx=scene["tanfovx"], tanfovy=scene["tanfovy"],
+                          kernel_size=scene["kernel_size"], subpixel_offset=d["subpixel_offset"], bg=d["bg"],
+                          scale_modifier=1.0, viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"],
+                          sh_degree=scene["sh_degree"], campos=d["campos"], prefiltered=False, debug=False,
+                          return_accumulation=True)
+        leaves = {k: d[k].requires_grad_(True) for k in leaves_k}
+        means2D = torch.zeros((P, 3), device=dev, requires_grad=True)
+        rast = parallel.ShardedGaussianRasterizer(st, bands=bands)
+        img, radii, acc = rast(means3D=leaves["means3D"], means2D=means2D, opacities=leaves["opacities"],
+                               shs=leaves.get("shs"), colors_precomp=leaves.get("colors_precomp"),
+                               scales=leaves.get("scales"), rotations=leaves.get("rotations"))
+        (img * d["dL_dpix"]).sum().backward()
+        parallel.download_sharded(img.detach(), out_host["image"])
+        parallel.download_sharded(means2D.grad, out_host["means2D"])
+        for k in leaves_k:
+            parallel.download_sharded(leaves[k].grad, out_host[k])
+        torch.cuda.current_stream(dev).synchronize()     # this rank's share of the step's result is on the host
+    return step, h2d, d2h
+
+
 def make_e2e_step(mod_api, scene, dev, settings_cls, sharded=None):
     """Public-API step with host buffers: H2D of every tensor argument from pinned memory, forward, backward,
     D2H of the image and of every gradient into pinned memory."""
@@ -287,9 +324,10 @@ def main():
             "data": "synthetic (seeded, SURVEY.md 8d generator)",
             "config": {"workload": workload, "P": P, "W": W, "H": H, "tiles": T,
                        "l2": "inputs_larger_than_l2 (per-step working set >= 0.5 GB vs 126 MB L2)",
-                       "parallelism": "single GPU" if world == 1 else f"tile-row bands x{world}, NCCL all-gather (image) + " + (
-                           "all-reduce (partials)" if os.environ.get("GSR_PEER_REDUCE", "1") == "0" else
-                           "reduction fused into the backward composite over peer/multicast memory")}}
+                       "parallelism": "single GPU" if world == 1 else f"tile-row bands x{world}, " + (
+                           "NCCL all-gather (image) + all-reduce (partials)" if os.environ.get("GSR_PEER_REDUCE", "1") == "0" else
+                           "image all-gather fused into the forward composite and partial-gradient reduction fused into the "
+                           "backward composite over NVLink peer memory (symmetric memory; NCCL only for setup)")}}
 
     sampler = ClockSampler(local_rank)
 
@@ -349,17 +387,32 @@ def main():
     else:
         state = {}
         def step():
-            _C.set_tile_row_shard(*band)
-            R, color, radii, geom, binning, img = _C.rasterize_gaussians(*call_args(d))
-            off = (128 - img.data_ptr()) % 128
-            fT = img[off:off + 4 * N].view(torch.float32).view(1, H, W)
-            full = parallel.gather_image_bands(torch.cat([color, fT], 0), bands)
-            bargs = backward_args(d, radii, geom, R, binning, img)
-            accum = parallel.reduced_partials(bargs, P, dev)
-            grads = _C.rasterize_gaussians_backward_finalize(accum, *bargs)
-            _C.set_tile_row_shard(0, 0)
-            state.update(R=R, radii=radii, geom=geom, binning=binning, img=img)
+            full, R, radii, geom, binning, img = parallel.sharded_forward(call_args(d), bands)
+            grads = parallel.sharded_backward(backward_args(d, radii, geom, R, binning, img), bands)
+            state.update(R=R, radii=radii, geom=geom, binning=binning, img=img, full=full, grads=grads)
 
+    check = None
+    if world > 1:
+        # SCALE carries its own correctness: the sharded result of THIS run against the single-GPU result on the same
+        # tensors (image bit for bit, gradients within the atomics tolerance), on every rank
+        step()
+        torch.cuda.synchronize(dev)
+        R1, color1, radii1, geom1, binning1, img1 = _C.rasterize_gaussians(*call_args(d))
+        g1 = _C.rasterize_gaussians_backward_lean(*backward_args(d, radii1, geom1, R1, binning1, img1))
+        torch.cuda.synchronize(dev)
+        ok_img = bool(torch.equal(state["full"][:3], color1)) and bool(torch.equal(state["radii"], radii1))
+        worst = 0.0
+        for a_, b_ in zip(state["grads"], g1):
+            if a_ is None or b_ is None or b_.numel() == 0:
+                continue
+            worst = max(worst, float((a_ - b_).abs().max()) / (float(b_.abs().max()) + 1e-30))
+        flags = torch.tensor([1.0 if ok_img else 0.0, worst], dtype=torch.float64, device=dev)
+        mn = flags.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        mx = flags.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        check = {"image_and_radii_bit_identical_to_single_gpu_on_every_rank": bool(mn[0].item() == 1.0),
+                 "max_gradient_rel_err_over_ranks": float(mx[1].item()), "gradient_tolerance": 1e-3,
+                 "passed": bool(mn[0].item() == 1.0 and mx[1].item() < 1e-3)}
+        del R1, color1, radii1, geom1, binning1, img1, g1
     launches0 = _C.launch_count()
     sampler.start()
     ms = time_steps(step, a.steps, a.warmup, dev, world)
@@ -459,6 +512,7 @@ def main():
             line["roofline"] = None
             line["roofline_note"] = f"not computed: {type(e).__name__}: {e}"
         line["bands"] = bands
+        line["check"] = check
 
     # wild-gaussians' step composites the same Gaussians twice (raw + appearance-toned colours,
     # method.py:1573-1611): two forwards + two backwards, with and without reuse of the first pass's geometry/binning
@@ -489,13 +543,16 @@ def main():
 
     # e2e through the public API with host buffers
     if not a.no_e2e:
-        sharded = None
         if world > 1:
-            sharded = lambda st: parallel.ShardedGaussianRasterizer(st, bands=bands)
-        e_step, h2d, d2h = make_e2e_step(GaussianRasterizer, scene, dev, GaussianRasterizationSettings, sharded)
+            e_step, h2d, d2h = make_e2e_step_sharded(scene, dev, GaussianRasterizationSettings, bands)
+        else:
+            e_step, h2d, d2h = make_e2e_step(GaussianRasterizer, scene, dev, GaussianRasterizationSettings, None)
         e_ms = time_steps(e_step, max(3, a.steps // 2), 3, dev, world)
         line["e2e"] = {"value": P * N / (e_ms * 1e-3), "unit": line["unit"], "ms_per_step": e_ms,
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        if world > 1:
+            line["e2e"]["note"] = ("whole-job bytes per step; each rank moves 1/world of every tensor over its own PCIe link "
+                                   "(parallel.upload_sharded / download_sharded), NVLink all-gathers the inputs")
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a.config, kw)

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 1
+#define GSR_ABI_VERSION 2
 
 /* negative status codes (positive values are cudaError_t) */
 #define GSR_E_INVALID      (-1)  /* bad argument (NULL where required, P<0, ...)            */
@@ -90,6 +90,13 @@ typedef struct GsrForwardArgs {
     /* outputs */
     float* out_color;             /* [3,H,W]  (rows of the shard are written)               */
     int*   radii;                 /* [P]      screen radius in px, 0 = not rendered         */
+    /* Multi-GPU image all-gather fused into the composite (optional): `peer_images` is a DEVICE array of
+     * `n_peer_images` pointers, one per rank (this rank included), each to a [4,H,W] fp32 image (colour planes +
+     * final transmittance) in peer-mapped memory (NVLink / NVSwitch symmetric memory).  The composite then stores
+     * every pixel of its band into ALL of them instead of out_color (which may be NULL); after a barrier across the
+     * ranks every rank holds the full image.  NULL / 0: single-GPU behaviour.                                   */
+    const void* const* peer_images;
+    int    n_peer_images;
 } GsrForwardArgs;
 
 /* Inputs/outputs of the backward pass.  Field meaning follows
@@ -121,7 +128,10 @@ typedef struct GsrBackwardArgs {
     const float* dL_dpix;         /* [3,H,W] upstream gradient of out_color                 */
     int debug;
     int tile_y0, tile_y1;         /* same shard as the forward                              */
-    void*  accum_scratch;         /* gsr_backward_scratch_bytes(P) bytes, need not be zeroed */
+    void*  accum_scratch;         /* gsr_backward_scratch_bytes(P) bytes.  gsr_backward / _partials zero it first unless
+                                     accum_is_zero != 0; gsr_backward_finalize leaves it ZEROED again (every row it
+                                     consumes is cleared), so a caller that keeps the buffer can skip the fill.       */
+    int    accum_is_zero;
     /* outputs */
     float* dL_dmean2D;            /* [P,3]  x,y: NDC-scaled screen grad; z: sum |gx|+|gy|
                                      (backward.cu:590-595)                                  */

@@ -37,16 +37,41 @@ def eval_sh(deg, sh, dirs):
     return res
 
 
-def colors(features_dc, features_rest, embeddings, app_embedding, W1, b1, W2, b2, W3, b3, means3D, campos, deg):
-    """(raw [P,3], toned [P,3]) exactly as GaussianModel._render_internal computes them."""
+def _bf16(x):
+    """Round to bfloat16 and back (straight-through gradient): how csrc/appearance.cu feeds the tensor cores."""
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+def mlp_bf16(color, embeddings, app_embedding, W1, b1, W2, b2, W3, b3):
+    """The 59 -> 128 -> 128 -> 6 MLP with the OPERAND ROUNDING of csrc/appearance.cu (fp32 tensors): inputs, weights
+    and hidden activations rounded to bf16, products exact and sums in fp32 (tcgen05 kind::f16), biases kept to
+    ~2^-17 (bias_hi + bias_lo), the image embedding folded into the first bias in fp32.  Same function as the fp32 MLP
+    up to that rounding -- but its ReLU masks are those of the rounded network, which is what a gradient check of the
+    kernel needs (a mask flipped by rounding changes a gradient entry by O(1): the gradient of a network with kinks
+    is not continuous in the weights' precision)."""
+    nd = color.shape[-1] + embeddings.shape[-1]
+    bias1 = b1 + W1[:, nd:] @ app_embedding
+    x = _bf16(torch.cat((color, embeddings), dim=-1))
+    h = _bf16(torch.relu(x @ _bf16(W1[:, :nd]).T + bias1))
+    h = _bf16(torch.relu(h @ _bf16(W2).T + b2))
+    return h @ _bf16(W3).T + b3
+
+
+def colors(features_dc, features_rest, embeddings, app_embedding, W1, b1, W2, b2, W3, b3, means3D, campos, deg,
+           emulate_bf16=False):
+    """(raw [P,3], toned [P,3]) exactly as GaussianModel._render_internal computes them (emulate_bf16: with the MLP
+    operand rounding of the CUDA kernel, see mlp_bf16)."""
     P = features_dc.shape[0]
     features = torch.cat((features_dc, features_rest), dim=-1).clamp_max(1.0)
     dirs = torch.nn.functional.normalize(means3D - campos[None].expand(P, 3), dim=1)
     raw = torch.clamp_min(eval_sh(deg, features.view(-1, 16, 3).transpose(1, 2), dirs) + 0.5, 0.0)
-    inp = torch.cat((features[..., :3], embeddings, app_embedding[None].expand(P, -1)), dim=-1)
-    h = torch.relu(inp @ W1.T + b1)
-    h = torch.relu(h @ W2.T + b2)
-    out = (h @ W3.T + b3) * 0.01
+    if emulate_bf16:
+        out = mlp_bf16(features[..., :3], embeddings, app_embedding, W1, b1, W2, b2, W3, b3) * 0.01
+    else:
+        inp = torch.cat((features[..., :3], embeddings, app_embedding[None].expand(P, -1)), dim=-1)
+        h = torch.relu(inp @ W1.T + b1)
+        h = torch.relu(h @ W2.T + b2)
+        out = (h @ W3.T + b3) * 0.01
     offset, mul = out[:, :3], out[:, 3:]
     offset = torch.cat((offset / C0, torch.zeros_like(features[..., 3:])), dim=-1)
     toned_f = (features * mul.repeat(1, 16) + offset).clamp_max(1.0)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(LIB)
     for fn in declared_functions():
         assert hasattr(lib, fn), f"{fn} declared in gsrast.h but not exported"
-    assert lib.gsr_abi_version() == 1
+    assert lib.gsr_abi_version() == 2
 
 
 def test_no_torch_types_in_boundary():

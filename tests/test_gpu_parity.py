@@ -510,7 +510,7 @@ def test_geometry_cache_hits_with_a_non_contiguous_view_matrix(C, dev):
     ref = run_ours(C, d)                                        # (its backward drops the cache entry)
     assert torch.equal(ref["color"], c1) and torch.equal(ref["radii"], radii2)
     R3, *_ = C.rasterize_gaussians(*args)
-    assert C.geometry_cache_hits() == h0 + 1                    # entry was released when the backward started
+    assert C.geometry_cache_hits() == h0 + 2                    # (run_ours' forward hit too) the entry was released when its backward started
 
 
 def test_async_forward_capacity_overflow_is_retried(C, dev):
@@ -520,6 +520,7 @@ def test_async_forward_capacity_overflow_is_retried(C, dev):
     scene = synthetic.make_scene(P=60_000, W=480, H=320, sh_degree=None, seed=52)
     d = synthetic.to_device(scene, dev)
     C.set_geometry_cache(False)
+    C.set_async_forward(True)
     C._size_hint.clear()
     first = run_ours(C, d)                                   # no hint: gsr_forward_geometry + gsr_forward_render
     key = next(iter(C._size_hint))
@@ -537,4 +538,5 @@ def test_async_forward_capacity_overflow_is_retried(C, dev):
         for n in ("dL_dmeans3D", "dL_dcolors"):
             assert rel_err(o["grads"][n].cpu().numpy(), first["grads"][n].cpu().numpy()) < 1e-5
     assert C._counters.get("overflow_retries", 0) == n0 + 4
+    C.set_async_forward(False)
     C.set_geometry_cache(True)

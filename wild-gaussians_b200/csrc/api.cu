@@ -137,7 +137,8 @@ static int check_fwd_args(const GsrForwardArgs* a) {
     if (a->P < 0 || a->W <= 0 || a->H <= 0) { set_error("bad sizes P=%d W=%d H=%d", a->P, a->W, a->H); return GSR_E_INVALID; }
     if (a->P > 0) {
         if (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix || !a->background || !a->subpixel_offset ||
-            !a->out_color || !a->radii) { set_error("a required pointer is NULL"); return GSR_E_INVALID; }
+            (!a->out_color && !a->peer_images) || !a->radii) { set_error("a required pointer is NULL"); return GSR_E_INVALID; }
+        if ((a->peer_images != nullptr) != (a->n_peer_images > 0)) { set_error("peer_images / n_peer_images mismatch"); return GSR_E_INVALID; }
         if ((a->shs == nullptr) == (a->colors_precomp == nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return GSR_E_INVALID; }
         const bool have_sr = a->scales != nullptr && a->rotations != nullptr;
         if (have_sr == (a->cov3D_precomp != nullptr) || ((a->scales != nullptr) != (a->rotations != nullptr))) {
@@ -440,7 +441,7 @@ static int check_bwd_args(const GsrBackwardArgs* a, bool need_pix, bool need_out
     return 0;
 }
 
-static BwdAccum* accum_of(const GsrBackwardArgs* a) {
+static BwdAccum* accum_of(const GsrBackwardArgs* a) {   // finalize clears the rows it consumes
     char* cur = (char*)a->accum_scratch;
     BwdAccum* accum;
     take(cur, accum, (size_t)a->P);
@@ -462,7 +463,7 @@ static int backward_partials_impl(const GsrBackwardArgs* a, void* stream, const 
     shard_rows(a->H, a->tile_y0, a->tile_y1, &ty0, &ty1);
     BwdAccum* accum = accum_of(a);
     // with peer accumulators the caller zeroes them (all ranks, then a barrier) before any rank adds into them
-    if (!peer) GSR_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * sizeof(BwdAccum), s));
+    if (!peer && !a->accum_is_zero) GSR_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * sizeof(BwdAccum), s));
     const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
     if (a->R > 0) {
         prof_begin(ST_RENDER_BWD, s);

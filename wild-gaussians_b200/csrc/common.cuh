@@ -154,7 +154,7 @@ struct PeerAccum {
 int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinState& b, const ImgState& im,
                       const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s,
                       const PeerAccum* peer = nullptr);
-int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, const BwdAccum* accum, cudaStream_t s);
+int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum* accum, cudaStream_t s);
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
 

@@ -35,6 +35,10 @@ struct RenderFwdParams {
     float* final_T;
     uint32_t* n_contrib;
     float* out_color;
+    // multi-GPU: the band is stored into the [4,H,W] images (colour + final transmittance) of ALL ranks through
+    // peer-mapped pointers (image all-gather fused into the composite's epilogue); NULL / 0 = local out_color only
+    float* const* peer_out;
+    int n_peers;
 };
 
 template <int PPT>
@@ -341,19 +345,25 @@ __global__ void __launch_bounds__(128) render_fwd_packed_kernel(const __grid_con
 
     const size_t plane = (size_t)p.H * p.W;
     const float bg0 = p.bg[0], bg1 = p.bg[1], bg2 = p.bg[2];
-    if (inside[0]) {
-        p.final_T[pix_id[0]] = T.x;
-        p.n_contrib[pix_id[0]] = last0;
-        p.out_color[0 * plane + pix_id[0]] = C0.x + T.x * bg0;
-        p.out_color[1 * plane + pix_id[0]] = C1.x + T.x * bg1;
-        p.out_color[2 * plane + pix_id[0]] = C2.x + T.x * bg2;
-    }
-    if (inside[1]) {
-        p.final_T[pix_id[1]] = T.y;
-        p.n_contrib[pix_id[1]] = last1;
-        p.out_color[0 * plane + pix_id[1]] = C0.y + T.y * bg0;
-        p.out_color[1 * plane + pix_id[1]] = C1.y + T.y * bg1;
-        p.out_color[2 * plane + pix_id[1]] = C2.y + T.y * bg2;
+    const float r0 = C0.x + T.x * bg0, g0 = C1.x + T.x * bg1, b0 = C2.x + T.x * bg2;
+    const float r1 = C0.y + T.y * bg0, g1 = C1.y + T.y * bg1, b1 = C2.y + T.y * bg2;
+    if (inside[0]) { p.final_T[pix_id[0]] = T.x; p.n_contrib[pix_id[0]] = last0; }
+    if (inside[1]) { p.final_T[pix_id[1]] = T.y; p.n_contrib[pix_id[1]] = last1; }
+    if (p.n_peers > 0) {
+        for (int r = 0; r < p.n_peers; ++r) {
+            float* img = p.peer_out[r];
+            if (inside[0]) {
+                img[0 * plane + pix_id[0]] = r0; img[1 * plane + pix_id[0]] = g0; img[2 * plane + pix_id[0]] = b0;
+                img[3 * plane + pix_id[0]] = T.x;
+            }
+            if (inside[1]) {
+                img[0 * plane + pix_id[1]] = r1; img[1 * plane + pix_id[1]] = g1; img[2 * plane + pix_id[1]] = b1;
+                img[3 * plane + pix_id[1]] = T.y;
+            }
+        }
+    } else {
+        if (inside[0]) { p.out_color[0 * plane + pix_id[0]] = r0; p.out_color[1 * plane + pix_id[0]] = g0; p.out_color[2 * plane + pix_id[0]] = b0; }
+        if (inside[1]) { p.out_color[0 * plane + pix_id[1]] = r1; p.out_color[1 * plane + pix_id[1]] = g1; p.out_color[2 * plane + pix_id[1]] = b1; }
     }
 }
 
@@ -379,6 +389,7 @@ int launch_render_fwd(const GsrForwardArgs& a, const GeomState& g, const BinStat
     p.subpixel_offset = reinterpret_cast<const float2*>(a.subpixel_offset);
     p.rec = g.rec; p.colors = colors; p.bg = a.background;
     p.final_T = im.final_T; p.n_contrib = im.n_contrib; p.out_color = a.out_color;
+    p.peer_out = (float* const*)(a.peer_images); p.n_peers = a.n_peer_images;
     if (ty1 <= ty0) return 0;
     dim3 grid(p.grid_x, ty1 - ty0, 1);
     static int packed = -1;
@@ -386,7 +397,7 @@ int launch_render_fwd(const GsrForwardArgs& a, const GeomState& g, const BinStat
         const char* e = getenv("GSR_FWD_PACKED");     // tuning aid: 1 = 2 pixels/lane in paired fp32 instructions
         packed = e ? atoi(e) : 1;
     }
-    if (packed) {
+    if (packed || p.n_peers > 0) {      // the fused all-gather epilogue exists in the packed kernel only
         render_fwd_packed_kernel<<<grid, 128, 0, s>>>(p);
         count_launches(1);
         return 0;

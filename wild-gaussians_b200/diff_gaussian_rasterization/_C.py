@@ -29,7 +29,7 @@ class GsrForwardArgs(Structure):
         ("cov3D_precomp", c_void_p), ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p),
         ("tan_fovx", c_float), ("tan_fovy", c_float), ("kernel_size", c_float), ("subpixel_offset", c_void_p),
         ("prefiltered", c_int), ("debug", c_int), ("tile_y0", c_int), ("tile_y1", c_int),
-        ("out_color", c_void_p), ("radii", c_void_p),
+        ("out_color", c_void_p), ("radii", c_void_p), ("peer_images", c_void_p), ("n_peer_images", c_int),
     ]
 
 
@@ -42,7 +42,7 @@ class GsrBackwardArgs(Structure):
         ("tan_fovx", c_float), ("tan_fovy", c_float), ("kernel_size", c_float), ("subpixel_offset", c_void_p),
         ("radii", c_void_p), ("geom_buffer", c_void_p), ("binning_buffer", c_void_p), ("img_buffer", c_void_p),
         ("dL_dpix", c_void_p), ("debug", c_int), ("tile_y0", c_int), ("tile_y1", c_int),
-        ("accum_scratch", c_void_p),
+        ("accum_scratch", c_void_p), ("accum_is_zero", c_int),
         ("dL_dmean2D", c_void_p), ("dL_dconic", c_void_p), ("dL_dopacity", c_void_p), ("dL_dcolor", c_void_p),
         ("dL_dmean3D", c_void_p), ("dL_dcov3D", c_void_p), ("dL_dsh", c_void_p), ("dL_dscale", c_void_p),
         ("dL_drot", c_void_p),
@@ -112,8 +112,8 @@ def _load():
                  "gsr_mark_visible", "gsr_img_views", "gsr_binning_views",
                  "gsr_geom_views", "gsr_get_stats"):
         getattr(lib, name).restype = c_int
-    if lib.gsr_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {lib.gsr_abi_version()} != 1")
+    if lib.gsr_abi_version() != 2:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.gsr_abi_version()} != 2")
     return lib
 
 
@@ -143,7 +143,18 @@ def get_tile_row_shard():
 # a backward pass starts (no further forward on this geometry can follow before the parameters change).
 _size_hint: dict = {}      # (P, W, H, shard) -> (instance capacity, coarse-item capacity) for the next call
 _counters: dict = {}       # bookkeeping: "overflow_retries"
-_ASYNC_FORWARD = os.environ.get("GSR_ASYNC_FORWARD", "1") != "0"
+# GSR_ASYNC_FORWARD=1: enqueue the whole forward on capacity-sized buffers and read the counts back at its END
+# (gsr_forward_async + gsr_forward_status) instead of the two-phase protocol with the read-back in the middle.  Off by
+# default: in a training loop the two-phase read-back costs one ~10 us bubble per step (everything after it is already
+# queued behind the GPU), whereas a synchronisation at the end of the forward exposes the host-side work between the
+# forward and the backward (measured at C3: 1.75 ms/step two-phase, 1.79 ms/step with the end-of-forward read-back).
+# The asynchronous entry point is what a CUDA-graph capture of the forward needs.
+_ASYNC_FORWARD = os.environ.get("GSR_ASYNC_FORWARD", "0") != "0"
+
+
+def set_async_forward(on: bool) -> None:
+    global _ASYNC_FORWARD
+    _ASYNC_FORWARD = bool(on)
 _GEOM_CACHE_ON = os.environ.get("GSR_GEOM_CACHE", "1") != "0"
 _geom_cache: dict = {}
 
@@ -223,8 +234,10 @@ def _abi_shard(shard, H):
 
 def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scales, rotations, scale_modifier,
                               cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
-                              image_height, image_width, sh, degree, campos, prefiltered, debug):
-    """``rasterize_gaussians`` restricted to the tile rows ``shard = (y0, y1)`` ((0, 0): whole image)."""
+                              image_height, image_width, sh, degree, campos, prefiltered, debug, peer_images=None):
+    """``rasterize_gaussians`` restricted to the tile rows ``shard = (y0, y1)`` ((0, 0): whole image).
+    ``peer_images = (device address of the array of per-rank [4,H,W] image pointers, number of ranks)``: the band is
+    stored into the images of all ranks by the composite itself (``out_color`` is then returned as None)."""
     if means3D.ndimension() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -241,7 +254,7 @@ def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scale
         # every pixel of the rendered rows and every radii entry is written by the kernels: the reference's
         # zero-fills (rasterize_points.cu:67-68) are only needed for the rows a tile-row shard leaves out
         alloc_img = torch.empty if shard == (0, 0) else torch.zeros
-        out_color = alloc_img((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
+        out_color = None if peer_images is not None else alloc_img((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
         M = int(sh.size(1)) if sh.numel() != 0 else 0
         stream = _stream(dev)
         gb, ib = c_size_t(0), c_size_t(0)
@@ -255,7 +268,7 @@ def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scale
         scalars = (float(scale_modifier), float(tan_fovx), float(tan_fovy), float(kernel_size), int(bool(prefiltered)),
                    int(bool(debug)))
         geo_key = _geometry_key(dev, stream, P, W, H, M, scalars, shard, geo_orig)
-        hit = _geom_cache.get("entry") if (_GEOM_CACHE_ON and M == 0) else None
+        hit = _geom_cache.get("entry") if (_GEOM_CACHE_ON and M == 0 and peer_images is None) else None
         if hit is not None and not (hit["key"] == geo_key and all(
                 (x is y) or (x.numel() == 0 and y.numel() == 0)      # "absent" inputs are fresh empty tensors per call
                 for x, y in zip(hit["orig"], geo_orig))):
@@ -280,7 +293,9 @@ def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scale
         a.kernel_size = float(kernel_size); a.subpixel_offset = _ptr(subpixel_offset)
         a.prefiltered = int(bool(prefiltered)); a.debug = int(bool(debug))
         a.tile_y0, a.tile_y1 = shard
-        a.out_color = out_color.data_ptr()
+        a.out_color = None if out_color is None else out_color.data_ptr()
+        if peer_images is not None:
+            a.peer_images, a.n_peer_images = int(peer_images[0]), int(peer_images[1])
 
         if hit is not None:
             img2 = torch.empty((ib.value,), **byte)
@@ -334,7 +349,7 @@ def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scale
         # `scratch` goes back to torch's stream-ordered caching allocator here: any later
         # allocation on this stream is ordered after the kernels that use it.
         del scratch
-        if _GEOM_CACHE_ON and M == 0:
+        if _GEOM_CACHE_ON and M == 0 and peer_images is None:
             _geom_cache["entry"] = dict(
                 key=geo_key, orig=geo_orig,
                 conv=(means3D, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, subpixel_offset),
@@ -381,9 +396,9 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
         (background, means3D, colors, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, subpixel_offset,
          dL_dout_color, sh, campos) = keep
         radii = radii.contiguous()
-        if accum is None:
-            # [P,12] fp32 partial sums; +64 floats so a 256-byte aligned view of P rows always fits
-            accum = torch.empty((P * 12 + 64,), **f32)
+        own_accum = accum is None
+        if own_accum:
+            accum = _zero_accumulator(P, dev)
         assert accum.data_ptr() % 256 == 0 and accum.numel() >= P * 12
 
         a = GsrBackwardArgs()
@@ -398,6 +413,7 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
         a.dL_dpix = _ptr(dL_dout_color); a.debug = int(bool(debug))
         a.tile_y0, a.tile_y1 = _abi_shard(_shard if shard is None else shard, H)
         a.accum_scratch = accum.data_ptr()
+        a.accum_is_zero = 1 if (own_accum or peer is not None) else 0
         if outs is not None:
             a.dL_dmean2D = dL_dmeans2D.data_ptr(); a.dL_dconic = None
             a.dL_dopacity = dL_dopacity.data_ptr(); a.dL_dcolor = dL_dcolors.data_ptr()
@@ -413,8 +429,35 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
             return accum
         fn = {"both": _lib.gsr_backward, "partials": _lib.gsr_backward_partials,
               "finalize": _lib.gsr_backward_finalize}[mode]
+        if mode != "finalize":
+            _accum_state[id(accum)] = "dirty"          # until a finalize has consumed (and thereby cleared) it
         _check(fn(byref(a), _stream(dev)), "gsr_backward" + ("" if mode == "both" else "_" + mode))
+        if mode != "partials":
+            _accum_state[id(accum)] = "zero"
     return accum if mode == "partials" else outs
+
+
+# ---- the [P,12] partial-sum accumulator of the backward ----------------------------------------------------------------
+# gsr_backward_finalize clears every row it consumes, so the buffer is all-zero again after each complete backward: it is
+# kept per (device, stream, P) and handed to the next pass with accum_is_zero = 1 (no 48 B x P fill, no allocation).  A
+# pass that was started but never finalised (an exception in between) leaves it marked dirty and it is re-zeroed.
+_accum_cache: dict = {}
+_accum_state: dict = {}
+
+
+def _zero_accumulator(P, dev):
+    key = (str(dev), int(_stream(dev)), int(P))
+    t = _accum_cache.get(key)
+    if t is None:
+        if len(_accum_cache) >= 4:
+            _accum_cache.clear(); _accum_state.clear()
+        # +64 floats so a 256-byte aligned view of P rows always fits
+        t = _accum_cache[key] = torch.zeros((P * 12 + 64,), dtype=torch.float32, device=dev)
+        _accum_state[id(t)] = "zero"
+    elif _accum_state.get(id(t)) != "zero":
+        t.zero_()
+        _accum_state[id(t)] = "zero"
+    return t
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,

@@ -85,34 +85,84 @@ def reduce_partials(accum: torch.Tensor, group=None) -> torch.Tensor:
     return accum
 
 
-# ---- reduction fused into the backward composite (peer / multicast memory over NVLink-NVSwitch) -----------------
-# GSR_PEER_REDUCE=1 (default): every rank's backward composite adds its per-Gaussian sums straight into the accumulators
-# of all ranks through peer pointers (torch symmetric memory over NVLink); =2: through the NVSwitch multicast address
-# when the platform offers one (one multimem.red per 16 bytes, the switch updates every replica); =0: NCCL all-reduce
-# of the partial arrays after the kernel.  Measured at C3 (profiles/): 2 GPUs 1.65 (NCCL) / 1.35 (peer) / 1.42 ms
-# (multicast); 4 GPUs 1.46 / 1.13 / 1.19 ms.  If symmetric memory cannot be set up the NCCL path is used.
+# ---- collectives fused into the composites (peer / multicast memory over NVLink-NVSwitch) --------------------------------
+# Forward: every rank's composite stores its band of the [4,H,W] image (colour + final transmittance) straight into the
+# symmetric image buffer of EVERY rank (peer-mapped pointers); one device-side barrier later each rank holds the full
+# image -- no NCCL call, no staging copies.
+# Backward: GSR_PEER_REDUCE=1 (default): every rank's backward composite adds its per-Gaussian sums straight into the
+# accumulators of all ranks through peer pointers; =2: through the NVSwitch multicast address when the platform offers
+# one (one multimem.red per 16 bytes, the switch updates every replica); =0: local sums + NCCL all-reduce after the kernel
+# (and a NCCL all-gather of the image bands in the forward).  The accumulators stay zero between steps: the per-Gaussian
+# chain-rule kernel clears every row it consumes (no fill, no extra barrier).  If symmetric memory cannot be set up the
+# NCCL path is used.
 _PEER_MODE = int(os.environ.get("GSR_PEER_REDUCE", "1"))
 _peer_state: dict = {}
 _peer_warned = False
 
 
-def _peer_accumulator(P: int, device, group):
-    """This rank's symmetric [P,12] fp32 accumulator (+ handle), created once per (P, device, group)."""
-    import torch.distributed._symmetric_memory as symm_mem
-    key = (int(P), str(device), id(group))
-    st = _peer_state.get(key)
-    if st is None:
-        t = symm_mem.empty(P * 12 + 64, dtype=torch.float32, device=device)
-        hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
-        mc = 0
+class _PeerState:
+    """Symmetric buffers of one (P, H, W, device, group): the [P,12] accumulator and the [4,H,W] image."""
+
+    def __init__(self, P, H, W, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        g = group if group is not None else dist.group.WORLD
+        self.accum = symm_mem.empty(P * 12 + 64, dtype=torch.float32, device=device)
+        self.accum.zero_()
+        self.accum_hdl = symm_mem.rendezvous(self.accum, g)
+        self.image = symm_mem.empty(4 * H * W, dtype=torch.float32, device=device)
+        self.image_hdl = symm_mem.rendezvous(self.image, g)
+        self.mc = 0
         if _PEER_MODE >= 2:
             try:
-                mc = int(hdl.multicast_ptr or 0)
+                self.mc = int(self.accum_hdl.multicast_ptr or 0)
             except Exception:
-                mc = 0
-        assert t.data_ptr() % 256 == 0 and all(int(x) % 256 == 0 for x in hdl.buffer_ptrs)
-        st = _peer_state[key] = (t, hdl, mc)
+                self.mc = 0
+        assert self.accum.data_ptr() % 256 == 0 and all(int(x) % 256 == 0 for x in self.accum_hdl.buffer_ptrs)
+        self.world = self.accum_hdl.world_size
+        # every rank's accumulator is zero before anyone adds into it
+        self.accum_hdl.barrier(channel=0)
+
+
+def _peers(P, H, W, device, group):
+    """The symmetric state, or None when the NCCL path has to be used."""
+    global _peer_warned
+    if _PEER_MODE <= 0 or P <= 0 or dist.get_backend(group) != "nccl":
+        return None
+    key = (int(P), int(H), int(W), str(device), id(group))
+    st = _peer_state.get(key)
+    if st is None and key not in _peer_state:
+        try:
+            st = _PeerState(P, H, W, device, group)
+        except Exception as e:                      # no symmetric memory on this platform / build: NCCL path
+            st = None
+            if not _peer_warned:
+                _peer_warned = True
+                print(f"[parallel] symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL collectives")
+        _peer_state[key] = st
     return st
+
+
+def sharded_forward(fwd_args, bands, group=None):
+    """This rank's band of one forward + the image all-gather.  ``fwd_args``: the 21 positional arguments of
+    ``_C.rasterize_gaussians``.  Returns ``(full [4,H,W] (colour planes + final transmittance), num_rendered, radii, geom,
+    binning, img)``; the full image is identical on every rank."""
+    from diff_gaussian_rasterization import _C
+    rank = dist.get_rank(group)
+    means3D = fwd_args[1]
+    P, H, W = int(means3D.size(0)), int(fwd_args[14]), int(fwd_args[15])
+    shard = tuple(bands[rank])
+    st = _peers(P, H, W, means3D.device, group)
+    if st is not None:
+        R, _none, radii, geom, binning, img = _C.rasterize_gaussians_shard(
+            shard, *fwd_args, peer_images=(st.image_hdl.buffer_ptrs_dev, st.world))
+        st.image_hdl.barrier(channel=0)             # every band has landed in every rank's image
+        full = st.image.view(4, H, W).clone()       # the symmetric buffer is overwritten by the next forward
+        return full, R, radii, geom, binning, img
+    R, color, radii, geom, binning, img = _C.rasterize_gaussians_shard(shard, *fwd_args)
+    offset = (128 - img.data_ptr()) % 128
+    final_T = img[offset:offset + 4 * H * W].view(torch.float32).view(1, H, W)
+    full = gather_image_bands(torch.cat([color, final_T], dim=0), bands, group)
+    return full, R, radii, geom, binning, img
 
 
 def reduced_partials(bwd_args, P: int, device, group=None, shard=None) -> torch.Tensor:
@@ -120,26 +170,30 @@ def reduced_partials(bwd_args, P: int, device, group=None, shard=None) -> torch.
     per-Gaussian sums (flat fp32, first P*12 entries).  Either NCCL all-reduce of the partial arrays or, with
     GSR_PEER_REDUCE, the reduction fused into the kernel through peer / multicast memory."""
     from diff_gaussian_rasterization import _C
-    st = None
-    if _PEER_MODE > 0 and P > 0 and dist.get_backend(group) == "nccl":
-        try:
-            st = _peer_accumulator(P, device, group)
-        except Exception as e:                      # no symmetric memory on this platform / build: NCCL path
-            global _peer_warned
-            if not _peer_warned:
-                _peer_warned = True
-                print(f"[parallel] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce")
+    H, W = int(bwd_args[14].size(1)), int(bwd_args[14].size(2))
+    st = _peers(P, H, W, device, group)
     if st is not None:
-        accum, hdl, mc = st
-        accum.zero_()
-        hdl.barrier(channel=0)          # every rank's accumulator is clean before anyone adds into it
-        _C.rasterize_gaussians_backward_partials_peers(accum, hdl.buffer_ptrs_dev, hdl.world_size, mc, *bwd_args,
+        # the accumulators of all ranks are zero here: cleared by the previous step's chain-rule kernel (or at creation),
+        # and the forward's image barrier lies between that kernel and this one on every rank
+        _C.rasterize_gaussians_backward_partials_peers(st.accum, st.accum_hdl.buffer_ptrs_dev, st.world, st.mc, *bwd_args,
                                                        shard=shard)
-        hdl.barrier(channel=1)          # all contributions have landed everywhere
-        return accum
+        st.accum_hdl.barrier(channel=1)          # all contributions have landed everywhere
+        return st.accum
     accum = _C.rasterize_gaussians_backward_partials(*bwd_args, shard=shard)
     reduce_partials(accum[: P * 12], group)
     return accum
+
+
+def sharded_backward(bwd_args, bands, group=None):
+    """Backward of ``sharded_forward``: ``bwd_args`` are the 23 positional arguments of
+    ``_C.rasterize_gaussians_backward`` (upstream gradient replicated); returns the 8 gradient tensors, complete on every
+    rank."""
+    from diff_gaussian_rasterization import _C
+    rank = dist.get_rank(group)
+    means3D = bwd_args[1]
+    shard = tuple(bands[rank])
+    accum = reduced_partials(bwd_args, int(means3D.size(0)), means3D.device, group, shard=shard)
+    return _C.rasterize_gaussians_backward_finalize(accum, *bwd_args, shard=shard)
 
 
 class _ShardedRasterize(torch.autograd.Function):
@@ -148,9 +202,7 @@ class _ShardedRasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 raster_settings, bands, group):
-        from diff_gaussian_rasterization import _C
         s = raster_settings
-        rank = dist.get_rank(group)
         args = (s.bg, means3D, colors_precomp, opacities, scales, rotations, s.scale_modifier, cov3Ds_precomp,
                 s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size, s.subpixel_offset,
                 s.image_height, s.image_width, sh, s.sh_degree, s.campos, s.prefiltered, s.debug)
@@ -162,19 +214,15 @@ class _ShardedRasterize(torch.autograd.Function):
             return z, torch.zeros((0,), dtype=torch.int32, device=dev), (torch.zeros((H, W), dtype=torch.float32, device=dev)
                                                                          if s.return_accumulation else None)
         ctx.empty = False
-        # the band is an explicit argument of the call (stored on ctx for the backward), not module state
-        num_rendered, color, radii, geom, binning, img = _C.rasterize_gaussians_shard(tuple(bands[rank]), *args)
-        offset = (128 - img.data_ptr()) % 128
-        final_T = img[offset:offset + 4 * H * W].view(torch.float32).view(1, H, W)
-        full = gather_image_bands(torch.cat([color, final_T], dim=0), bands, group)
+        # the band is an explicit argument of the calls (stored on ctx for the backward), not module state
+        full, num_rendered, radii, geom, binning, img = sharded_forward(args, bands, group)
         ctx.raster_settings, ctx.num_rendered, ctx.bands, ctx.group = s, num_rendered, bands, group
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom, binning, img)
         accumulation = (1.0 - full[3]) if s.return_accumulation else None
-        return full[:3].contiguous(), radii, accumulation
+        return full[:3], radii, accumulation
 
     @staticmethod
     def backward(ctx, grad_out_color, _1, _2):
-        from diff_gaussian_rasterization import _C
         s = ctx.raster_settings
         if ctx.empty:
             return (None,) * 11
@@ -182,12 +230,37 @@ class _ShardedRasterize(torch.autograd.Function):
         args = (s.bg, means3D, radii, colors_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp,
                 s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.kernel_size, s.subpixel_offset,
                 grad_out_color, sh, s.sh_degree, s.campos, geom, ctx.num_rendered, binning, img, s.debug)
-        rank = dist.get_rank(ctx.group)
-        shard = tuple(ctx.bands[rank])
-        accum = reduced_partials(args, int(means3D.size(0)), means3D.device, ctx.group, shard=shard)
-        (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot) = \
-            _C.rasterize_gaussians_backward_finalize(accum, *args, shard=shard)
+        (g_means2D, g_colors, g_opac, g_means3D, g_cov3D, g_sh, g_scales, g_rot) = sharded_backward(args, ctx.bands, ctx.group)
         return (g_means3D, g_means2D, g_sh, g_colors, g_opac, g_scales, g_rot, g_cov3D, None, None, None)
+
+
+# ---- host-buffer I/O for the sharded path: every rank moves only 1/world of the bytes over PCIe ---------------------------
+def upload_sharded(host: torch.Tensor, device, group=None) -> torch.Tensor:
+    """`host` is a pinned CPU tensor holding the SAME data on every rank.  Rank r copies only the r-th of `world` equal
+    chunks of its bytes to the device; one all-gather (NVLink) assembles the full tensor on every rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    flat = host.reshape(-1)
+    n = flat.numel()
+    chunk = (n + world - 1) // world
+    full = torch.empty((chunk * world,), dtype=host.dtype, device=device)
+    lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+    mine = full[rank * chunk: rank * chunk + (hi - lo)]
+    if hi > lo:
+        mine.copy_(flat[lo:hi], non_blocking=True)
+    dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk].clone(), group=group)
+    return full[:n].view(host.shape)
+
+
+def download_sharded(dev_t: torch.Tensor, host_out: torch.Tensor, group=None) -> None:
+    """Counterpart of ``upload_sharded`` for results that are replicated on every rank (image, gradients): rank r copies
+    only its chunk into its pinned `host_out`; the ranks' host buffers together hold the tensor exactly once."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    flat, out = dev_t.reshape(-1), host_out.reshape(-1)
+    n = flat.numel()
+    chunk = (n + world - 1) // world
+    lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+    if hi > lo:
+        out[lo:hi].copy_(flat[lo:hi], non_blocking=True)
 
 
 class ShardedGaussianRasterizer(torch.nn.Module):
