@@ -593,6 +593,13 @@ def full_train_step(kw, dev, steps, impl="ours"):
         for name, rcls, scls in arms:
             wh.use_backend(m, rcls, scls)
             res[name] = time_steps(lambda: wh.train_step(model, cfg, cam, G1, G2), steps, 3, dev, 1)
+        # opt-in fused caller (wildgaussians_fused.enable): fused tcgen05 colour op + cached camera constants, same
+        # rasterizer, method.py still unmodified
+        import wildgaussians_fused as wf
+        wh.use_backend(m, ours.GaussianRasterizer, ours.GaussianRasterizationSettings)
+        wf.enable(model)
+        res["ours_fused_caller_ms"] = time_steps(lambda: wh.train_step(model, cfg, cam, G1, G2), steps, 3, dev, 1)
+        wf.disable(model)
     finally:
         wh.use_backend(m, ours.GaussianRasterizer, ours.GaussianRasterizationSettings)
         ours._C.set_geometry_cache(False)

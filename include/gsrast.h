@@ -129,8 +129,8 @@ typedef struct GsrBackwardArgs {
     int debug;
     int tile_y0, tile_y1;         /* same shard as the forward                              */
     void*  accum_scratch;         /* gsr_backward_scratch_bytes(P) bytes.  gsr_backward / _partials zero it first unless
-                                     accum_is_zero != 0; gsr_backward_finalize leaves it ZEROED again (every row it
-                                     consumes is cleared), so a caller that keeps the buffer can skip the fill.       */
+                                     accum_is_zero != 0; gsr_backward_finalize leaves it ZEROED again (a stream-
+                                     ordered fill after its kernel), so a caller that keeps the buffer skips the fill. */
     int    accum_is_zero;
     /* outputs */
     float* dL_dmean2D;            /* [P,3]  x,y: NDC-scaled screen grad; z: sum |gx|+|gy|
@@ -276,6 +276,14 @@ int gsr_appearance_colors_backward(const GsrAppearanceArgs* args, void* stream);
 int gsr_appearance_unpack_grads(const float* grad_pack, const float* W1, const float* appearance_embedding, float* dW1,
                                 float* db1, float* dW2, float* db2, float* dW3, float* db3,
                                 float* dappearance_embedding, void* stream);
+
+/* -- densification statistics (optional entry point) -----------------------------------------------------
+ * One pass over the Gaussians replacing wildgaussians/method.py:1997-1998 + GaussianModel.add_densification_stats
+ * (:1470-1477): for every Gaussian with radii > 0: max_radii2D = max(., radii); xyz_grad += |grad.xy|;
+ * accum_abs += |grad.z|; accum_abs_max = max(., |grad.z|) (both NULL when use_gof_abs_gradient is off); denom += 1.
+ * viewspace_grad is the [P,3] gradient the rasterizer leaves in means2D.grad (summed over the step's passes).          */
+int gsr_densification_stats(int P, const int* radii, const float* viewspace_grad, float* max_radii2D, float* xyz_grad,
+                            float* xyz_gradient_accum_abs, float* xyz_gradient_accum_abs_max, float* denom, void* stream);
 
 /* Optional per-stage device timing (cudaEvents on the caller's stream around each stage of the
  * next forward / backward calls).  The caller synchronises the stream, then reads the stage times of

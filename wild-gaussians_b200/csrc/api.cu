@@ -441,7 +441,7 @@ static int check_bwd_args(const GsrBackwardArgs* a, bool need_pix, bool need_out
     return 0;
 }
 
-static BwdAccum* accum_of(const GsrBackwardArgs* a) {   // finalize clears the rows it consumes
+static BwdAccum* accum_of(const GsrBackwardArgs* a) {
     char* cur = (char*)a->accum_scratch;
     BwdAccum* accum;
     take(cur, accum, (size_t)a->P);
@@ -501,6 +501,10 @@ int gsr_backward_finalize(const GsrBackwardArgs* a, void* stream) {
     if (rc) return rc;
     GSR_STAGE(s, a->debug != 0, "preprocess_bwd_kernel");
     prof_end(ST_PREPROCESS_BWD, s);
+    // leave the accumulator zeroed for the next backward pass (stream-ordered fill AFTER its only reader): a caller that
+    // keeps the buffer passes accum_is_zero = 1 next time, and the tile-row sharded path needs no fill + barrier in front
+    // of its peer reductions.  (Clearing the consumed rows inside the kernel was measured 3.5x slower for the kernel.)
+    GSR_CUDA(cudaMemsetAsync(accum_of(a), 0, (size_t)a->P * sizeof(BwdAccum), s));
     return 0;
 }
 

@@ -31,7 +31,7 @@ struct PreBwdParams {
     const float* proj;
     const float* campos;
     const float4* rec;
-    float* accum;           // [P][12]; the rows of rendered Gaussians are consumed AND cleared (left zero for the next pass)
+    const float* accum;     // [P][12]
     float* dL_dmean2D;      // [P,3]
     float* dL_dconic;       // [P,4] or NULL
     float* dL_dopacity;     // [P]
@@ -209,11 +209,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
     bool sh_written = false;
 
     if (rendered) {
-        float4* acc = reinterpret_cast<float4*>(p.accum + (size_t)idx * 12);
+        const float4* acc = reinterpret_cast<const float4*>(p.accum + (size_t)idx * 12);
         const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2];
-        // only rows of rendered Gaussians are ever added to (render_bwd.cu): clearing them here keeps the whole
-        // accumulator zero between backward passes, so no 48 B x P fill precedes the next one
-        acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         o_mean2D[0] = a0.x; o_mean2D[1] = a0.y; o_mean2D[2] = a0.z;
         o_conic[0] = a0.w; o_conic[1] = a1.x; o_conic[3] = a1.y;
         float dL_dopacity = a1.z;
@@ -450,7 +447,7 @@ int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum
     p.means3D = a.means3D; p.radii = a.radii; p.shs = a.shs; p.clamped = g.clamped;
     p.scales = a.scales; p.rotations = a.rotations; p.cov3D_precomp = a.cov3D_precomp;
     p.view = a.viewmatrix; p.proj = a.projmatrix; p.campos = a.campos;
-    p.rec = g.rec; p.accum = reinterpret_cast<float*>(accum);
+    p.rec = g.rec; p.accum = reinterpret_cast<const float*>(accum);
     p.dL_dmean2D = a.dL_dmean2D; p.dL_dconic = a.dL_dconic; p.dL_dopacity = a.dL_dopacity;
     p.dL_dcolor = a.dL_dcolor; p.dL_dmean3D = a.dL_dmean3D; p.dL_dcov3D = a.dL_dcov3D;
     p.dL_dsh = a.dL_dsh; p.dL_dscale = a.dL_dscale; p.dL_drot = a.dL_drot;

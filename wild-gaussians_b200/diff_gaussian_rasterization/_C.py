@@ -99,6 +99,8 @@ def _load():
     for name in ("gsr_appearance_pack_weights", "gsr_appearance_colors_forward", "gsr_appearance_colors_backward",
                  "gsr_appearance_unpack_grads"):
         getattr(lib, name).restype = c_int
+    lib.gsr_densification_stats.argtypes = [c_int] + [c_void_p] * 8
+    lib.gsr_densification_stats.restype = c_int
     lib.gsr_profile_enable.argtypes = [c_int]
     lib.gsr_profile_enable.restype = None
     lib.gsr_profile_stage_count.restype = c_int
@@ -438,7 +440,7 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
 
 
 # ---- the [P,12] partial-sum accumulator of the backward ----------------------------------------------------------------
-# gsr_backward_finalize clears every row it consumes, so the buffer is all-zero again after each complete backward: it is
+# gsr_backward_finalize zero-fills the buffer after consuming it, so it is all-zero again after each complete backward: it is
 # kept per (device, stream, P) and handed to the next pass with accum_is_zero = 1 (no 48 B x P fill, no allocation).  A
 # pass that was started but never finalised (an exception in between) leaves it marked dirty and it is re-zeroed.
 _accum_cache: dict = {}

@@ -93,7 +93,7 @@ def reduce_partials(accum: torch.Tensor, group=None) -> torch.Tensor:
 # accumulators of all ranks through peer pointers; =2: through the NVSwitch multicast address when the platform offers
 # one (one multimem.red per 16 bytes, the switch updates every replica); =0: local sums + NCCL all-reduce after the kernel
 # (and a NCCL all-gather of the image bands in the forward).  The accumulators stay zero between steps: the per-Gaussian
-# chain-rule kernel clears every row it consumes (no fill, no extra barrier).  If symmetric memory cannot be set up the
+# chain-rule stage zero-fills its accumulator after consuming it (no fill + barrier in front of the reductions).  If symmetric memory cannot be set up the
 # NCCL path is used.
 _PEER_MODE = int(os.environ.get("GSR_PEER_REDUCE", "1"))
 _peer_state: dict = {}
