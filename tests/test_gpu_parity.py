@@ -540,3 +540,29 @@ def test_async_forward_capacity_overflow_is_retried(C, dev):
     assert C._counters.get("overflow_retries", 0) == n0 + 4
     C.set_async_forward(False)
     C.set_geometry_cache(True)
+
+
+def test_defer_composite_inputs_waits_before_the_composite(C, dev):
+    """Host-buffer pipelines: the forward may be started when only the geometry inputs are on the device; the composite
+    stage waits for the event that marks the arrival of colours / background / sub-pixel offsets."""
+    import diff_gaussian_rasterization as dgr
+    scene = synthetic.make_scene(P=30_000, W=320, H=208, sh_degree=None, seed=53, bg=(0.2, 0.1, 0.3), subpixel_jitter=0.4)
+    d = synthetic.to_device(scene, dev)
+    ref = run_ours(C, d)
+    C.set_geometry_cache(False)
+    side = torch.cuda.Stream(dev)
+    host = {k: scene[k].contiguous().pin_memory() for k in ("colors_precomp", "bg", "subpixel_offset")}
+    late = {k: torch.zeros_like(d[k]) for k in host}            # wrong values until the side stream has delivered
+    ev = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(200_000_000)                           # ~0.1 s: the copies land long after the forward was issued
+        for k in host:
+            late[k].copy_(host[k], non_blocking=True)
+        ev.record(side)
+    d2 = dict(d); d2.update(late)
+    dgr.defer_composite_inputs(ev)
+    R, color, radii, geom, binning, img = C.rasterize_gaussians(*call_args(d2))
+    torch.cuda.synchronize()
+    assert torch.equal(color, ref["color"]) and R == ref["R"]
+    assert C._render_wait["event"] is None                       # one-shot
+    C.set_geometry_cache(True)

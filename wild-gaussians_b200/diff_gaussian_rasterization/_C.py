@@ -222,6 +222,27 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                                      subpixel_offset, image_height, image_width, sh, degree, campos, prefiltered, debug)
 
 
+# ---- host-buffer pipelines: let the colour inputs arrive while the geometry stage runs ------------------------------------
+# The projection / depth-ordering / binning stages read only the geometry inputs (means, scales, rotations, opacities,
+# camera); colours, background and sub-pixel offsets are first read by the composite.  A caller that uploads its inputs
+# on a copy stream can therefore start the forward as soon as the geometry inputs have landed and hand over the event
+# that marks the arrival of the rest: the next forward on this thread waits for it right before its composite stage.
+_render_wait = {"event": None}
+
+
+def defer_composite_inputs(event) -> None:
+    """One-shot: the next forward waits for `event` (a torch.cuda.Event recorded on the stream that produces colours /
+    background / subpixel_offset) immediately before enqueueing its composite stage instead of before its first kernel."""
+    _render_wait["event"] = event
+
+
+def _wait_for_composite_inputs(dev):
+    ev = _render_wait["event"]
+    if ev is not None:
+        _render_wait["event"] = None
+        torch.cuda.current_stream(dev).wait_event(ev)
+
+
 def _abi_shard(shard, H):
     """(y0, y1) as the C ABI wants it: (0, 0) is its "whole image" sentinel, so an EMPTY band (a rank with no tile
     rows) is expressed as the empty band below the last row."""
@@ -300,6 +321,7 @@ def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scale
             a.peer_images, a.n_peer_images = int(peer_images[0]), int(peer_images[1])
 
         if hit is not None:
+            _wait_for_composite_inputs(dev)
             img2 = torch.empty((ib.value,), **byte)
             a.radii = hit["radii"].data_ptr()
             _check(_lib.gsr_forward_recolor(byref(a), hit["geom"].data_ptr(), hit["binning"].data_ptr(),
@@ -325,6 +347,7 @@ def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scale
         bb, sb = c_size_t(0), c_size_t(0)
         done = False
         if hint is not None and _ASYNC_FORWARD:
+            _wait_for_composite_inputs(dev)
             _check(_lib.gsr_binning_sizes(P, W, H, hint[0], hint[1], byref(bb), byref(sb)), "gsr_binning_sizes")
             binning = torch.empty((bb.value,), **byte)
             scratch = torch.empty((sb.value,), **byte)
@@ -340,6 +363,7 @@ def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scale
             _check(_lib.gsr_forward_geometry(byref(a), geom.data_ptr(), img.data_ptr(), stream, byref(R), byref(N1)),
                    "gsr_forward_geometry")
         if not done:
+            _wait_for_composite_inputs(dev)
             _check(_lib.gsr_binning_sizes(P, W, H, R.value, N1.value, byref(bb), byref(sb)), "gsr_binning_sizes")
             binning = torch.empty((bb.value,), **byte)
             scratch = torch.empty((sb.value,), **byte)

@@ -23,7 +23,10 @@ import torch.nn as nn
 
 from . import _C
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "defer_composite_inputs"]
+
+# extension of the reference surface for host-buffer pipelines (see _C.defer_composite_inputs)
+defer_composite_inputs = _C.defer_composite_inputs
 
 
 def cpu_deep_copy_tuple(input_tuple):

@@ -54,7 +54,9 @@ def _camera_constants(m, cam, device):
     T = pose[:3, 3]
     fx, fy, cx, cy = cam.intrinsics
     world_view = torch.tensor(m.getWorld2View2(R, T, np.array([0.0, 0.0, 0.0], dtype=np.float32), 1.0)).transpose(0, 1).to(device=device)
-    proj = m.getProjectionMatrixFromOpenCV(width, height, fx, fy, cx, cy, 0.01, 100.0).transpose(0, 1).to(device=device)
+    # (float() arguments: the helper assigns its results into a torch tensor element, which rejects numpy.float32 scalars)
+    proj = m.getProjectionMatrixFromOpenCV(width, height, float(fx), float(fy), float(cx), float(cy), 0.01, 100.0) \
+        .transpose(0, 1).to(device=device)
     full_proj = (world_view.unsqueeze(0).bmm(proj.unsqueeze(0))).squeeze(0)
     cam_center = world_view.inverse()[3, :3]
     out = dict(world_view=world_view.contiguous(), full_proj=full_proj.contiguous(), cam_center=cam_center.contiguous(),
