@@ -32,6 +32,7 @@
 // largest magnitude; tests/test_appearance.py states the bars.
 #include "common.cuh"
 #include "umma.cuh"
+#include "sh_math.cuh"
 
 namespace gsr {
 
@@ -54,11 +55,7 @@ constexpr uint32_t REST_BYTES = AP_TILE * AP_NREST * 4;                  // 2304
 constexpr size_t GW1P = 0, GW2P = GW1P + AP_H * AP_K1, GW3P = GW2P + AP_H * AP_K2, GB3 = GW3P + AP_H * AP_N3,
                  GPACK_FLOATS = GB3 + 16;
 
-constexpr float SH_C0 = 0.28209479177387814f, SH_C1 = 0.4886025119029199f;
-__constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
-                               0.5462742152960396f};
-__constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
-                               -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+constexpr float SH_C0 = SHK0;
 
 struct ApParams {
     int P, deg, num_tiles;
@@ -95,49 +92,6 @@ __device__ __forceinline__ uint64_t desc_k(const uint8_t* base, int kstep, uint3
 // MN-major operand (contraction over the rows of the image): k-th group of 16 rows
 __device__ __forceinline__ uint64_t desc_mn(const uint8_t* base, int kstep, uint32_t rows) {
     return smem_desc(smem_u32(base) + (uint32_t)kstep * 256u, 128u, rows * 16u);
-}
-
-// SH basis of eval_sh (method.py:493-548) for the active degree; entries above the degree are 0
-__device__ __forceinline__ void sh_basis(int deg, float x, float y, float z, float (&b)[16]) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) b[k] = 0.f;
-    b[0] = SH_C0;
-    if (deg > 0) {
-        b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
-        if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            b[4] = SH_C2[0] * xy; b[5] = SH_C2[1] * yz; b[6] = SH_C2[2] * (2.f * zz - xx - yy);
-            b[7] = SH_C2[3] * xz; b[8] = SH_C2[4] * (xx - yy);
-            if (deg > 2) {
-                b[9] = SH_C3[0] * y * (3.f * xx - yy); b[10] = SH_C3[1] * xy * z;
-                b[11] = SH_C3[2] * y * (4.f * zz - xx - yy); b[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-                b[13] = SH_C3[4] * x * (4.f * zz - xx - yy); b[14] = SH_C3[5] * z * (xx - yy);
-                b[15] = SH_C3[6] * x * (xx - 3.f * yy);
-            }
-        }
-    }
-}
-// sum_k g[k] * grad b_k(x, y, z)
-__device__ __forceinline__ float3 sh_basis_grad_dot(int deg, float x, float y, float z, const float (&g)[16]) {
-    float3 r = {0.f, 0.f, 0.f};
-    if (deg > 0) {
-        r.y += -SH_C1 * g[1]; r.z += SH_C1 * g[2]; r.x += -SH_C1 * g[3];
-        if (deg > 1) {
-            r.x += SH_C2[0] * y * g[4] - 2.f * SH_C2[2] * x * g[6] + SH_C2[3] * z * g[7] + 2.f * SH_C2[4] * x * g[8];
-            r.y += SH_C2[0] * x * g[4] + SH_C2[1] * z * g[5] - 2.f * SH_C2[2] * y * g[6] - 2.f * SH_C2[4] * y * g[8];
-            r.z += SH_C2[1] * y * g[5] + 4.f * SH_C2[2] * z * g[6] + SH_C2[3] * x * g[7];
-            if (deg > 2) {
-                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                r.x += SH_C3[0] * 6.f * xy * g[9] + SH_C3[1] * yz * g[10] - SH_C3[2] * 2.f * xy * g[11] - SH_C3[3] * 6.f * xz * g[12] +
-                       SH_C3[4] * (4.f * zz - 3.f * xx - yy) * g[13] + SH_C3[5] * 2.f * xz * g[14] + SH_C3[6] * 3.f * (xx - yy) * g[15];
-                r.y += SH_C3[0] * 3.f * (xx - yy) * g[9] + SH_C3[1] * xz * g[10] + SH_C3[2] * (4.f * zz - xx - 3.f * yy) * g[11] -
-                       SH_C3[3] * 6.f * yz * g[12] - SH_C3[4] * 2.f * xy * g[13] - SH_C3[5] * 2.f * yz * g[14] - SH_C3[6] * 6.f * xy * g[15];
-                r.z += SH_C3[1] * xy * g[10] + SH_C3[2] * 8.f * yz * g[11] + SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy) * g[12] +
-                       SH_C3[4] * 8.f * xz * g[13] + SH_C3[5] * (xx - yy) * g[14];
-            }
-        }
-    }
-    return r;
 }
 
 // ---- weight packing ----------------------------------------------------------------------------------------------
@@ -568,10 +522,10 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
             }
             // view direction -> mean (eval_sh is differentiated through `dir`, method.py:1572)
             const float3 dd = sh_basis_grad_dot(p.deg, in.dir.x, in.dir.y, in.dir.z, gk);
-            const float dot = dd.x * in.dir.x + dd.y * in.dir.y + dd.z * in.dir.z;
-            p.g_means[(size_t)row * 3 + 0] = (dd.x - in.dir.x * dot) * in.inv_norm;
-            p.g_means[(size_t)row * 3 + 1] = (dd.y - in.dir.y * dot) * in.inv_norm;
-            p.g_means[(size_t)row * 3 + 2] = (dd.z - in.dir.z * dot) * in.inv_norm;
+            const float3 dm = through_normalize(in.dir, in.inv_norm, dd);
+            p.g_means[(size_t)row * 3 + 0] = dm.x;
+            p.g_means[(size_t)row * 3 + 1] = dm.y;
+            p.g_means[(size_t)row * 3 + 2] = dm.z;
         }
         // dO (bf16) -> shared memory; bias gradient of the last layer = column sums of dO (fp32, warp shuffles)
         st_chunk(s_do, 0, t, make_uint4(pack_bf16(dOut[0], dOut[1]), pack_bf16(dOut[2], dOut[3]), pack_bf16(dOut[4], dOut[5]), 0u));

@@ -12,6 +12,7 @@
 // fp32 here (gradients are compared at 1e-3; see the comment in the kernel).
 #include "common.cuh"
 #include "gaussian_math.cuh"
+#include "sh_math.cuh"
 #include <cstdlib>
 
 namespace gsr {
@@ -43,33 +44,21 @@ struct PreBwdParams {
     float* dL_drot;         // [P,4] or NULL
 };
 
-// direction-normalisation Jacobian applied to dv (auxiliary.h:107-117)
-__device__ __forceinline__ float3 dnormvdv3(float3 v, float3 dv) {
-    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
-    const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
-    float3 r;
-    r.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
-    r.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
-    r.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
-    return r;
-}
-
-// SH colour backward (backward.cu:20-139): writes the dL_dsh row, returns the mean gradient caused by the view
-// direction.  `vec`: rows are aligned multiples of 16 bytes -- the coefficients are read and the gradient row is
-// written with 128-bit accesses (a scalar access pattern makes every instruction of a warp touch 32 sectors, one per
-// Gaussian, and the kernel becomes bound by L1/L2 sector traffic: measured 8x slower per Gaussian).
+// SH colour backward (what backward.cu:20-139 computes): colour_c = max(sum_k b_k(dir) sh[k][c] + 0.5, 0), so
+//   dL/dsh[k][c] = b_k(dir) * dL/dcolour_c            (0 for clamped channels and for k above the active degree)
+//   dL/ddir      = sum_k (sum_c dL/dcolour_c sh[k][c]) * grad b_k(dir),   then through dir = v / |v| to the mean.
+// Writes the dL_dsh row, returns the mean gradient caused by the view direction.  `vec`: rows are aligned multiples of
+// 16 bytes -- the coefficients are read and the gradient row is written with 128-bit accesses (a scalar access pattern
+// makes every instruction of a warp touch 32 sectors, one per Gaussian: measured 8x slower per Gaussian).
 __device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const float* __restrict__ sh_base, bool vec, float3 mean,
                                               const float* __restrict__ campos, unsigned clamp_bits, V3 dL_dRGB,
                                               float* __restrict__ dL_dsh_base) {
-    V3 pos = {mean.x, mean.y, mean.z};
-    V3 cam = {campos[0], campos[1], campos[2]};
-    V3 dir_orig = pos - cam;
-    const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-    V3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
-
-    dL_dRGB.x *= (clamp_bits & 1u) ? 0 : 1;
-    dL_dRGB.y *= (clamp_bits & 2u) ? 0 : 1;
-    dL_dRGB.z *= (clamp_bits & 4u) ? 0 : 1;
+    const float3 v = {mean.x - campos[0], mean.y - campos[1], mean.z - campos[2]};
+    const float inv_len = 1.0f / sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    const float3 dir = {v.x * inv_len, v.y * inv_len, v.z * inv_len};
+    if (clamp_bits & 1u) dL_dRGB.x = 0.f;
+    if (clamp_bits & 2u) dL_dRGB.y = 0.f;
+    if (clamp_bits & 4u) dL_dRGB.z = 0.f;
 
     const int used = (deg + 1) * (deg + 1);
     float shl[48];
@@ -79,8 +68,8 @@ __device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const flo
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
             if (i < n4) {
-                const float4 v = __ldg(p4 + i);
-                shl[4 * i + 0] = v.x; shl[4 * i + 1] = v.y; shl[4 * i + 2] = v.z; shl[4 * i + 3] = v.w;
+                const float4 q = __ldg(p4 + i);
+                shl[4 * i + 0] = q.x; shl[4 * i + 1] = q.y; shl[4 * i + 2] = q.z; shl[4 * i + 3] = q.w;
             }
         }
     } else {
@@ -88,70 +77,12 @@ __device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const flo
         for (int i = 0; i < 48; ++i)
             if (i < 3 * used) shl[i] = sh_base[i];
     }
-
-    V3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
-    const float x = dir.x, y = dir.y, z = dir.z;
-
-    auto sh = [&](int k) { return V3{shl[3 * k], shl[3 * k + 1], shl[3 * k + 2]}; };
-    // basis weight of every coefficient (0 above the active degree: those receive no gradient)
-    float w[16];
+    float w[16], g[16];
+    sh_basis(deg, dir.x, dir.y, dir.z, w);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) w[k] = 0.f;
+    for (int k = 0; k < 16; ++k)
+        g[k] = k < used ? dL_dRGB.x * shl[3 * k] + dL_dRGB.y * shl[3 * k + 1] + dL_dRGB.z * shl[3 * k + 2] : 0.f;
 
-    w[0] = GSR_SH_C0;
-    if (deg > 0) {
-        w[1] = -GSR_SH_C1 * y;
-        w[2] = GSR_SH_C1 * z;
-        w[3] = -GSR_SH_C1 * x;
-
-        dRGBdx = -GSR_SH_C1 * sh(3);
-        dRGBdy = -GSR_SH_C1 * sh(1);
-        dRGBdz = GSR_SH_C1 * sh(2);
-
-        if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z;
-            const float xy = x * y, yz = y * z, xz = x * z;
-            w[4] = GSR_SH_C2_0 * xy;
-            w[5] = GSR_SH_C2_1 * yz;
-            w[6] = GSR_SH_C2_2 * (2.f * zz - xx - yy);
-            w[7] = GSR_SH_C2_3 * xz;
-            w[8] = GSR_SH_C2_4 * (xx - yy);
-
-            dRGBdx += GSR_SH_C2_0 * y * sh(4) + GSR_SH_C2_2 * 2.f * -x * sh(6) + GSR_SH_C2_3 * z * sh(7) + GSR_SH_C2_4 * 2.f * x * sh(8);
-            dRGBdy += GSR_SH_C2_0 * x * sh(4) + GSR_SH_C2_1 * z * sh(5) + GSR_SH_C2_2 * 2.f * -y * sh(6) + GSR_SH_C2_4 * 2.f * -y * sh(8);
-            dRGBdz += GSR_SH_C2_1 * y * sh(5) + GSR_SH_C2_2 * 2.f * 2.f * z * sh(6) + GSR_SH_C2_3 * x * sh(7);
-
-            if (deg > 2) {
-                w[9] = GSR_SH_C3_0 * y * (3.f * xx - yy);
-                w[10] = GSR_SH_C3_1 * xy * z;
-                w[11] = GSR_SH_C3_2 * y * (4.f * zz - xx - yy);
-                w[12] = GSR_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
-                w[13] = GSR_SH_C3_4 * x * (4.f * zz - xx - yy);
-                w[14] = GSR_SH_C3_5 * z * (xx - yy);
-                w[15] = GSR_SH_C3_6 * x * (xx - 3.f * yy);
-
-                dRGBdx += (GSR_SH_C3_0 * sh(9) * 3.f * 2.f * xy +
-                           GSR_SH_C3_1 * sh(10) * yz +
-                           GSR_SH_C3_2 * sh(11) * -2.f * xy +
-                           GSR_SH_C3_3 * sh(12) * -3.f * 2.f * xz +
-                           GSR_SH_C3_4 * sh(13) * (-3.f * xx + 4.f * zz - yy) +
-                           GSR_SH_C3_5 * sh(14) * 2.f * xz +
-                           GSR_SH_C3_6 * sh(15) * 3.f * (xx - yy));
-                dRGBdy += (GSR_SH_C3_0 * sh(9) * 3.f * (xx - yy) +
-                           GSR_SH_C3_1 * sh(10) * xz +
-                           GSR_SH_C3_2 * sh(11) * (-3.f * yy + 4.f * zz - xx) +
-                           GSR_SH_C3_3 * sh(12) * -3.f * 2.f * yz +
-                           GSR_SH_C3_4 * sh(13) * -2.f * xy +
-                           GSR_SH_C3_5 * sh(14) * -2.f * yz +
-                           GSR_SH_C3_6 * sh(15) * -3.f * 2.f * xy);
-                dRGBdz += (GSR_SH_C3_1 * sh(10) * xy +
-                           GSR_SH_C3_2 * sh(11) * 4.f * 2.f * yz +
-                           GSR_SH_C3_3 * sh(12) * 3.f * (2.f * zz - xx - yy) +
-                           GSR_SH_C3_4 * sh(13) * 4.f * 2.f * xz +
-                           GSR_SH_C3_5 * sh(14) * (xx - yy));
-            }
-        }
-    }
     // dL_dsh[k][c] = w[k] * dL_dRGB[c]; coefficients above the active degree get 0 (w[k] = 0)
     if (vec) {
         float4* o4 = reinterpret_cast<float4*>(dL_dsh_base);
@@ -180,9 +111,7 @@ __device__ __forceinline__ float3 sh_backward(int deg, int max_coeffs, const flo
             dL_dsh_base[3 * k + 2] = 0.f;
         }
     }
-
-    const float3 dL_ddir = {dot3(dRGBdx, dL_dRGB), dot3(dRGBdy, dL_dRGB), dot3(dRGBdz, dL_dRGB)};
-    return dnormvdv3(float3{dir_orig.x, dir_orig.y, dir_orig.z}, dL_ddir);
+    return through_normalize(dir, inv_len, sh_basis_grad_dot(deg, dir.x, dir.y, dir.z, g));
 }
 
 template <int MIN_CTAS, bool HAS_SH>
@@ -231,124 +160,95 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
             cov3D = cov3D_local;
         }
 
-        // ---- 2D covariance / conic backward (backward.cu:144-310) ----
-        const float3 dL_dconic = {o_conic[0], o_conic[1], o_conic[3]};
+        // ---- screen-space covariance / conic / compensation backward (what backward.cu:144-310 computes) ----------
+        // Own derivation.  With the two rows t0, t1 of the 2x3 projection A = J W (columns 0 / 1 of the GLM matrix T):
+        //   cov2D = A Sigma A^T + k I = [[a, b], [b, c]],   conic = cov2D^-1,   opacity' = opacity * coef(cov2D).
         const float4 rb = p.rec[2 * (size_t)idx + 1];
-        const float combined_opacity = rb.w;
-        const float h_x = p.focal_x, h_y = p.focal_y;
+        const float fx = p.focal_x, fy = p.focal_y, ks = p.kernel_size;
+        const Ewa e = ewa_project(mean, fx, fy, p.tan_fovx, p.tan_fovy, cov3D, s_view);
+        const V3 t0 = {e.T.m[0][0], e.T.m[0][1], e.T.m[0][2]};
+        const V3 t1 = {e.T.m[1][0], e.T.m[1][1], e.T.m[1][2]};
+        const float ca0 = e.cov.m[0][0], b = e.cov.m[0][1], cc0 = e.cov.m[1][1];      // before the low-pass
+        const float a = ca0 + ks, c = cc0 + ks;
 
-        const Ewa e = ewa_project(mean, h_x, h_y, p.tan_fovx, p.tan_fovy, cov3D, s_view);
-        const float3 t = e.t;
-        const float x_grad_mul = e.txtz < -e.limx || e.txtz > e.limx ? 0 : 1;
-        const float y_grad_mul = e.tytz < -e.limy || e.tytz > e.limy ? 0 : 1;
-        const Mat3& T = e.T;
-        const Mat3& Vrk = e.Vrk;
-        Mat3 cov2D = e.cov;
-        const float kernel_size = p.kernel_size;
+        // (1) conic -> cov2D.  For K = cov^-1 and the symmetric gradient Gk = [[gx, gy], [gy, gz]] (gy is the
+        //     per-off-diagonal-entry gradient the composite accumulates), dL/dcov = -adj Gk adj / det^2 with
+        //     adj = [[c, -b], [-b, a]]; the reference regularises det^2 by + 1e-7 (backward.cu:229) -- kept.
+        const float gx = o_conic[0], gy = o_conic[1], gz = o_conic[3];
+        const float det = a * c - b * b;
+        const float N = 1.0f / (det * det + 0.0000001f);
+        float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+        if (N != 0.f) {
+            const float r0x = c * gx - b * gy, r0y = c * gy - b * gz;      // row 0 of adj Gk
+            const float r1x = a * gy - b * gx, r1y = a * gz - b * gy;      // row 1 of adj Gk
+            dL_da = -N * (r0x * c - r0y * b);
+            dL_db = -2.0f * N * (r0y * a - r0x * b);
+            dL_dc = -N * (r1y * a - r1x * b);
 
-        // Opacity-compensation gradient (backward.cu:199-217).  The reference evaluates this block in double
-        // because of its double literals; only gradients (compared at 1e-3) depend on it, so it is evaluated in
-        // fp32 here -- about 350 instructions of fp64 division / square root per Gaussian less.  The two clamps
-        // and the det <= 1e-6 tests below select exactly the same branch as the double comparisons: no float lies
-        // strictly between (float)1e-6 and 1e-6.
-        const float det_0 = fmaxf(1e-6f, cov2D.m[0][0] * cov2D.m[1][1] - cov2D.m[0][1] * cov2D.m[0][1]);
-        const float det_1 = fmaxf(1e-6f, (cov2D.m[0][0] + kernel_size) * (cov2D.m[1][1] + kernel_size) - cov2D.m[0][1] * cov2D.m[0][1]);
-        const float inv_det1e = 1.0f / (det_1 + 1e-6f);
-        const float coef = sqrtf(det_0 * inv_det1e + 1e-6f);
-
-        const float inv_coefe = 1.0f / (coef + 1e-6f);
-        const float opacity = combined_opacity * inv_coefe;
-        const float dL_dcoef = dL_dopacity * opacity;
-        const float dL_dsqrtcoef = dL_dcoef * 0.5f * inv_coefe;
-        const float dL_ddet0 = dL_dsqrtcoef * inv_det1e;
-        const float dL_ddet1 = dL_dsqrtcoef * det_0 * (-1.f / (det_1 * det_1 + 1e-6f));
-        const float dcoef_da = dL_ddet0 * cov2D.m[1][1] + dL_ddet1 * (cov2D.m[1][1] + kernel_size);
-        const float dcoef_db = dL_ddet0 * (-2.f * cov2D.m[0][1]) + dL_ddet1 * (-2.f * cov2D.m[0][1]);
-        const float dcoef_dc = dL_ddet0 * cov2D.m[0][0] + dL_ddet1 * (cov2D.m[0][0] + kernel_size);
-
-        const float a = cov2D.m[0][0] += kernel_size;
-        const float b = cov2D.m[0][1];
-        const float c = cov2D.m[1][1] += kernel_size;
-
-        const float denom = a * c - b * b;
-        float dL_da = 0, dL_db = 0, dL_dc = 0;
-        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-
-        if (denom2inv != 0) {
-            dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
-            dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
-            dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
-
-            if (det_0 <= 1e-6f || det_1 <= 1e-6f) {
-                dL_dopacity = 0;
+            // (2) opacity compensation coef = sqrt(det0 / (det1 + eps) + eps), det0 / det1 before / after the low-pass
+            //     (forward.cu:112-118; evaluated in fp32 here, the reference's mixed fp32 / fp64 only matters for the
+            //     forward's bit-exact opacity; its eps terms and its clamps at 1e-6 are kept)
+            const float det0 = fmaxf(1e-6f, ca0 * cc0 - b * b);
+            const float det1 = fmaxf(1e-6f, a * c - b * b);
+            if (det0 <= 1e-6f || det1 <= 1e-6f) {
+                dL_dopacity = 0.f;
             } else {
-                dL_da += dcoef_da;
-                dL_dc += dcoef_dc;
-                dL_db += dcoef_db;
-                dL_dopacity = dL_dopacity * coef;
+                const float inv1 = 1.0f / (det1 + 1e-6f);
+                const float coef = sqrtf(det0 * inv1 + 1e-6f);
+                const float inv_c = 1.0f / (coef + 1e-6f);
+                const float half = 0.5f * dL_dopacity * (rb.w * inv_c) * inv_c;       // dL/d(det0 / (det1 + eps))
+                const float d0 = half * inv1;                                          // dL/ddet0
+                const float d1 = -half * det0 / (det1 * det1 + 1e-6f);                 // dL/ddet1
+                dL_da += d0 * cc0 + d1 * c;
+                dL_db -= 2.0f * b * (d0 + d1);
+                dL_dc += d0 * ca0 + d1 * a;
+                dL_dopacity *= coef;
             }
-
-            o_cov3D[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
-            o_cov3D[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
-            o_cov3D[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
-            o_cov3D[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
-            o_cov3D[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
-            o_cov3D[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
         }
         o_opacity = dL_dopacity;
 
-        const float dL_dT00 = 2 * (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_da +
-                              (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_db;
-        const float dL_dT01 = 2 * (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_da +
-                              (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_db;
-        const float dL_dT02 = 2 * (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_da +
-                              (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_db;
-        const float dL_dT10 = 2 * (T.m[1][0] * Vrk.m[0][0] + T.m[1][1] * Vrk.m[0][1] + T.m[1][2] * Vrk.m[0][2]) * dL_dc +
-                              (T.m[0][0] * Vrk.m[0][0] + T.m[0][1] * Vrk.m[0][1] + T.m[0][2] * Vrk.m[0][2]) * dL_db;
-        const float dL_dT11 = 2 * (T.m[1][0] * Vrk.m[1][0] + T.m[1][1] * Vrk.m[1][1] + T.m[1][2] * Vrk.m[1][2]) * dL_dc +
-                              (T.m[0][0] * Vrk.m[1][0] + T.m[0][1] * Vrk.m[1][1] + T.m[0][2] * Vrk.m[1][2]) * dL_db;
-        const float dL_dT12 = 2 * (T.m[1][0] * Vrk.m[2][0] + T.m[1][1] * Vrk.m[2][1] + T.m[1][2] * Vrk.m[2][2]) * dL_dc +
-                              (T.m[0][0] * Vrk.m[2][0] + T.m[0][1] * Vrk.m[2][1] + T.m[0][2] * Vrk.m[2][2]) * dL_db;
-
-        // W (column-major): W[c][r] = view[4*r + c]
-        const float W00 = s_view[0], W01 = s_view[4], W02 = s_view[8];
-        const float W10 = s_view[1], W11 = s_view[5], W12 = s_view[9];
-        const float W20 = s_view[2], W21 = s_view[6], W22 = s_view[10];
-        const float dL_dJ00 = W00 * dL_dT00 + W01 * dL_dT01 + W02 * dL_dT02;
-        const float dL_dJ02 = W20 * dL_dT00 + W21 * dL_dT01 + W22 * dL_dT02;
-        const float dL_dJ11 = W10 * dL_dT10 + W11 * dL_dT11 + W12 * dL_dT12;
-        const float dL_dJ12 = W20 * dL_dT10 + W21 * dL_dT11 + W22 * dL_dT12;
-
-        const float tz = 1.f / t.z;
-        const float tz2 = tz * tz;
-        const float tz3 = tz2 * tz;
-
-        const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
-        const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
-        const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
-
-        // transformVec4x3Transpose (auxiliary.h:89-97)
-        float3 dL_dmean_cov = {
-            s_view[0] * dL_dtx + s_view[1] * dL_dty + s_view[2] * dL_dtz,
-            s_view[4] * dL_dtx + s_view[5] * dL_dty + s_view[6] * dL_dtz,
-            s_view[8] * dL_dtx + s_view[9] * dL_dty + s_view[10] * dL_dtz,
+        // (3) cov2D -> Sigma and -> the projection rows.  G = dL_da t0 t0^T + dL_db/2 (t0 t1^T + t1 t0^T) + dL_dc t1 t1^T
+        //     is dL/dSigma (rank 2); dL/dt0 = 2 dL_da Sigma t0 + dL_db Sigma t1, dL/dt1 = 2 dL_dc Sigma t1 + dL_db Sigma t0.
+        auto sym = [&](const V3& v) -> V3 {       // Sigma v, Sigma given by its upper triangle
+            return {cov3D[0] * v.x + cov3D[1] * v.y + cov3D[2] * v.z, cov3D[1] * v.x + cov3D[3] * v.y + cov3D[4] * v.z,
+                    cov3D[2] * v.x + cov3D[4] * v.y + cov3D[5] * v.z};
         };
+        const V3 u0 = sym(t0), u1 = sym(t1);
+        const V3 g0 = (2.0f * dL_da) * u0 + dL_db * u1;
+        const V3 g1 = (2.0f * dL_dc) * u1 + dL_db * u0;
+        if (N != 0.f) {      // stored like the reference: diagonal entries, and off-diagonals carrying both symmetric halves
+            o_cov3D[0] = dL_da * t0.x * t0.x + dL_db * t0.x * t1.x + dL_dc * t1.x * t1.x;
+            o_cov3D[3] = dL_da * t0.y * t0.y + dL_db * t0.y * t1.y + dL_dc * t1.y * t1.y;
+            o_cov3D[5] = dL_da * t0.z * t0.z + dL_db * t0.z * t1.z + dL_dc * t1.z * t1.z;
+            o_cov3D[1] = 2.0f * (dL_da * t0.x * t0.y + dL_dc * t1.x * t1.y) + dL_db * (t0.x * t1.y + t0.y * t1.x);
+            o_cov3D[2] = 2.0f * (dL_da * t0.x * t0.z + dL_dc * t1.x * t1.z) + dL_db * (t0.x * t1.z + t0.z * t1.x);
+            o_cov3D[4] = 2.0f * (dL_da * t0.y * t0.z + dL_dc * t1.y * t1.z) + dL_db * (t0.y * t1.z + t0.z * t1.y);
+        }
 
-        // ---- projective-divide backward of the screen-space mean (backward.cu:402-423) ----
+        // (4) projection rows -> view-space mean.  t0 = J00 w0 + J02 w2, t1 = J11 w1 + J12 w2 with w_r the view axes in world
+        //     coordinates and J00 = fx / z, J02 = -fx x / z^2, J11 = fy / z, J12 = -fy y / z^2 (x, y clamped to the frustum
+        //     guard band: no gradient to x / y where the clamp is active).
+        const V3 w0 = {s_view[0], s_view[4], s_view[8]}, w1 = {s_view[1], s_view[5], s_view[9]}, w2 = {s_view[2], s_view[6], s_view[10]};
+        const float dJ00 = dot3(w0, g0), dJ02 = dot3(w2, g0), dJ11 = dot3(w1, g1), dJ12 = dot3(w2, g1);
+        const float iz = 1.0f / e.t.z, iz2 = iz * iz, iz3 = iz2 * iz;
+        const bool x_free = !(e.txtz < -e.limx || e.txtz > e.limx), y_free = !(e.tytz < -e.limy || e.tytz > e.limy);
+        const float gvx = x_free ? -fx * iz2 * dJ02 : 0.f;
+        const float gvy = y_free ? -fy * iz2 * dJ12 : 0.f;
+        const float gvz = -iz2 * (fx * dJ00 + fy * dJ11) + 2.0f * iz3 * (fx * e.t.x * dJ02 + fy * e.t.y * dJ12);
+        const V3 dmean_cov = gvx * w0 + gvy * w1 + gvz * w2;
+
+        // (5) screen position (NDC-scaled gradient from the composite) -> mean, through the projective divide
+        //     ndc = (P m).xy / ((P m).w + 1e-7)   (forward.cu:210-212)
         const float* proj = s_proj;
-        const float3 m = mean;
-        const float4 m_hom = xform_point_4x4(m, proj);
-        const float m_w = 1.0f / (m_hom.w + 0.0000001f);
-        const float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
-        const float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
-        float3 dL_dmean;
-        dL_dmean.x = (proj[0] * m_w - proj[3] * mul1) * o_mean2D[0] + (proj[1] * m_w - proj[3] * mul2) * o_mean2D[1];
-        dL_dmean.y = (proj[4] * m_w - proj[7] * mul1) * o_mean2D[0] + (proj[5] * m_w - proj[7] * mul2) * o_mean2D[1];
-        dL_dmean.z = (proj[8] * m_w - proj[11] * mul1) * o_mean2D[0] + (proj[9] * m_w - proj[11] * mul2) * o_mean2D[1];
-
-        o_mean3D[0] = dL_dmean_cov.x + dL_dmean.x;
-        o_mean3D[1] = dL_dmean_cov.y + dL_dmean.y;
-        o_mean3D[2] = dL_dmean_cov.z + dL_dmean.z;
+        const float4 mh = xform_point_4x4(mean, proj);
+        const float iw = 1.0f / (mh.w + 0.0000001f);
+        const float nx = mh.x * iw, ny = mh.y * iw;                 // ndc.x, ndc.y
+        const float qx = o_mean2D[0] * iw, qy = o_mean2D[1] * iw, qw = -(qx * nx + qy * ny);
+        const V3 dmean_pos = {proj[0] * qx + proj[1] * qy + proj[3] * qw, proj[4] * qx + proj[5] * qy + proj[7] * qw,
+                              proj[8] * qx + proj[9] * qy + proj[11] * qw};
+        o_mean3D[0] = dmean_cov.x + dmean_pos.x;
+        o_mean3D[1] = dmean_cov.y + dmean_pos.y;
+        o_mean3D[2] = dmean_cov.z + dmean_pos.z;
 
         // ---- SH backward (backward.cu:20-139) ----
         if (HAS_SH) {
@@ -360,46 +260,31 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
             sh_written = true;
         }
 
-        // ---- cov3D -> scale / rotation backward (backward.cu:314-377) ----
+        // ---- Sigma -> scale / rotation (what backward.cu:314-377 computes) ----------------------------------------
+        // Sigma = sum_i s_i^2 r_i r_i^T with r_i the i-th local axis (row i of the GLM rotation matrix, raw quaternion,
+        // note N5) and s_i = modifier * scale_i.  With G of rank 2:  G r_i = al_i t0 + be_i t1,
+        //   al_i = dL_da (t0.r_i) + dL_db/2 (t1.r_i),  be_i = dL_db/2 (t0.r_i) + dL_dc (t1.r_i), so
+        //   dL/ds_i = 2 s_i r_i^T G r_i      (the reference applies no modifier factor here either)
+        //   h_i = dL/dr_i = 2 s_i^2 G r_i    and the quaternion gradient follows from the skew / symmetric parts of H = [h_i].
         if (p.scales != nullptr) {
-            const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+            const float qr = rot.x, qx = rot.y, qy = rot.z, qz = rot.w;
             const Mat3 R = quat_to_mat(rot);
-            Mat3 S = mat3_cols(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f);
-            const float3 s = {p.scale_modifier * sc.x, p.scale_modifier * sc.y, p.scale_modifier * sc.z};
-            S.m[0][0] = s.x;
-            S.m[1][1] = s.y;
-            S.m[2][2] = s.z;
-            const Mat3 M = mat3_mul(S, R);
-            const float* g6 = o_cov3D;
-            const Mat3 dL_dSigma = mat3_cols(
-                g6[0], 0.5f * g6[1], 0.5f * g6[2],
-                0.5f * g6[1], g6[3], 0.5f * g6[4],
-                0.5f * g6[2], 0.5f * g6[4], g6[5]);
-            // dL_dM = 2 * M * dL_dSigma  (scalar * matrix first, as GLM evaluates it)
-            Mat3 M2;
+            const float sv[3] = {p.scale_modifier * sc.x, p.scale_modifier * sc.y, p.scale_modifier * sc.z};
+            V3 h[3];
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc)
-#pragma unroll
-                for (int rr = 0; rr < 3; ++rr) M2.m[cc][rr] = 2.0f * M.m[cc][rr];
-            const Mat3 dL_dM = mat3_mul(M2, dL_dSigma);
-            const Mat3 Rt = mat3_transpose(R);
-            Mat3 dL_dMt = mat3_transpose(dL_dM);
-
-            o_scale[0] = Rt.m[0][0] * dL_dMt.m[0][0] + Rt.m[0][1] * dL_dMt.m[0][1] + Rt.m[0][2] * dL_dMt.m[0][2];
-            o_scale[1] = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
-            o_scale[2] = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
-
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                dL_dMt.m[0][k] *= s.x;
-                dL_dMt.m[1][k] *= s.y;
-                dL_dMt.m[2][k] *= s.z;
+            for (int i = 0; i < 3; ++i) {
+                const V3 r = {R.m[0][i], R.m[1][i], R.m[2][i]};
+                const float pi = dot3(t0, r), qi = dot3(t1, r);
+                const float al = dL_da * pi + 0.5f * dL_db * qi, be = 0.5f * dL_db * pi + dL_dc * qi;
+                o_scale[i] = 2.0f * sv[i] * (al * pi + be * qi);
+                h[i] = (2.0f * sv[i] * sv[i]) * (al * t0 + be * t1);
             }
-
-            o_rot[0] = 2 * z * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * y * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) + 2 * x * (dL_dMt.m[1][2] - dL_dMt.m[2][1]);
-            o_rot[1] = 2 * y * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * z * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) + 2 * r * (dL_dMt.m[1][2] - dL_dMt.m[2][1]) - 4 * x * (dL_dMt.m[2][2] + dL_dMt.m[1][1]);
-            o_rot[2] = 2 * x * (dL_dMt.m[1][0] + dL_dMt.m[0][1]) + 2 * r * (dL_dMt.m[2][0] - dL_dMt.m[0][2]) + 2 * z * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * y * (dL_dMt.m[2][2] + dL_dMt.m[0][0]);
-            o_rot[3] = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) + 2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
+            const float ax = h[1].z - h[2].y, ay = h[2].x - h[0].z, az = h[0].y - h[1].x;      // skew part
+            const float sxy = h[0].y + h[1].x, sxz = h[0].z + h[2].x, syz = h[1].z + h[2].y;   // symmetric part
+            o_rot[0] = 2.0f * (qx * ax + qy * ay + qz * az);
+            o_rot[1] = 2.0f * (qr * ax + qy * sxy + qz * sxz) - 4.0f * qx * (h[1].y + h[2].z);
+            o_rot[2] = 2.0f * (qr * ay + qx * sxy + qz * syz) - 4.0f * qy * (h[0].x + h[2].z);
+            o_rot[3] = 2.0f * (qr * az + qx * sxz + qy * syz) - 4.0f * qz * (h[0].x + h[1].y);
         }
     }
 
