@@ -277,6 +277,18 @@ int gsr_appearance_unpack_grads(const float* grad_pack, const float* W1, const f
                                 float* db1, float* dW2, float* db2, float* dW3, float* db3,
                                 float* dappearance_embedding, void* stream);
 
+/* -- parameter activations + 3D filter (optional entry points) --------------------------------------------
+ * GaussianModel.get_gaussians (wildgaussians/method.py:1060-1086) in one kernel per direction: rotations = normalize(raw),
+ * scales = sqrt(exp(raw)^2 + filter_3D^2), opacities = sigmoid(raw) * sqrt(prod(exp(raw)^2) / prod(exp(raw)^2 + filter_3D^2)).
+ * All arrays fp32, [P,3] / [P] / [P,4] (16-byte aligned) / [P].  The backward recomputes the forward; upstream gradients may be
+ * NULL (treated as zero).                                                                                                  */
+int gsr_gaussian_activations_forward(int P, const float* scales_raw, const float* opacities_raw, const float* rotations_raw,
+                                     const float* filter_3D, float* scales, float* opacities, float* rotations, void* stream);
+int gsr_gaussian_activations_backward(int P, const float* scales_raw, const float* opacities_raw, const float* rotations_raw,
+                                      const float* filter_3D, const float* dL_dscales, const float* dL_dopacities,
+                                      const float* dL_drotations, float* dL_dscales_raw, float* dL_dopacities_raw,
+                                      float* dL_drotations_raw, void* stream);
+
 /* -- densification statistics (optional entry point) -----------------------------------------------------
  * One pass over the Gaussians replacing wildgaussians/method.py:1997-1998 + GaussianModel.add_densification_stats
  * (:1470-1477): for every Gaussian with radii > 0: max_radii2D = max(., radii); xyz_grad += |grad.xy|;

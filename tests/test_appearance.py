@@ -162,3 +162,35 @@ def test_fused_colors_rejects_other_shapes_and_cpu():
     with pytest.raises(RuntimeError, match="CUDA"):
         fc.fused_colors(torch.zeros(10, 3), torch.zeros(10, 45), torch.zeros(10, 24), torch.zeros(32), mlp.cpu(),
                         torch.zeros(10, 3), torch.zeros(3), 3)
+
+
+def test_fused_activations_against_torch_statements():
+    """gsr_gaussian_activations_{forward,backward} against the statements of GaussianModel.get_gaussians
+    (method.py:1060-1086) in torch fp32: outputs and gradients within 1e-5 / 1e-4 relative."""
+    import fused_colors as fc
+    dev = torch.device("cuda:0")
+    P = 200_003
+    g = torch.Generator().manual_seed(9)
+    s = (torch.randn(P, 3, generator=g) * 0.7 - 3.0).to(dev)
+    o = (torch.randn(P, 1, generator=g) * 2.0).to(dev)
+    r = torch.randn(P, 4, generator=g).to(dev)
+    f = (torch.rand(P, 1, generator=g) * 0.05).to(dev)
+    gs, go, gr = (torch.randn(*t.shape, generator=g).to(dev) for t in (s, o, r))
+
+    def ref(s, o, r):
+        rot = torch.nn.functional.normalize(r)
+        raw = torch.exp(s)
+        scales = (torch.square(raw) + torch.square(f)).sqrt()
+        coef = torch.sqrt(torch.square(raw).prod(dim=1) / (torch.square(raw) + torch.square(f)).prod(dim=1))
+        return scales, torch.sigmoid(o) * coef[..., None], rot
+
+    res = []
+    for fn in (lambda a, b, c: fc.fused_activations(a, b, c, f), ref):
+        L = [t.clone().requires_grad_(True) for t in (s, o, r)]
+        out = fn(*L)
+        torch.autograd.backward(list(out), [gs, go, gr])
+        res.append(([x.detach() for x in out], [t.grad for t in L]))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert float((a - b).abs().max()) < 1e-5 * max(1.0, float(b.abs().max()))
+    for a, b in zip(res[0][1], res[1][1]):
+        assert float((a - b).abs().max()) < 1e-4 * max(1.0, float(b.abs().max()))

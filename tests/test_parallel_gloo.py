@@ -81,3 +81,45 @@ def test_gather_and_reduce_world2():
     for rank, ok_img, err, _, _ in res:
         assert ok_img, f"rank {rank}: gathered image differs from the single-rank image"
         assert err < 1e-6, f"rank {rank}: reduced partials differ ({err})"
+
+
+def _io_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import parallel
+        g = torch.Generator().manual_seed(5)
+        ok = True
+        for shape in ((1001, 3), (7,), (3, 50, 70), (4, 4)):
+            host = torch.randn(*shape, generator=g)              # same data on every rank
+            full = parallel.upload_sharded(host, torch.device("cpu"))
+            ok = ok and torch.equal(full, host)
+            out = torch.full(shape, float("nan"))
+            parallel.download_sharded(full * 2, out)
+            # every rank wrote exactly its chunk; together the chunks tile the tensor
+            flat = out.reshape(-1)
+            n = flat.numel(); chunk = (n + world - 1) // world
+            lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+            mine = torch.zeros(n, dtype=torch.bool); mine[lo:hi] = True
+            ok = ok and bool(torch.equal(flat[mine], (host.reshape(-1) * 2)[mine])) and bool(torch.isnan(flat[~mine]).all())
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_host_io_world2():
+    """parallel.upload_sharded / download_sharded (the multi-GPU e2e path: every rank moves 1/world of each tensor) on
+    gloo, world_size 2: the all-gathered tensor equals the host tensor; the ranks' downloads tile the result."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_io_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)

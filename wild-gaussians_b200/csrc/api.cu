@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 
 namespace gsr {
 
@@ -42,6 +43,7 @@ static unsigned long long g_launches = 0;
 void count_launches(int n) { g_launches += (unsigned long long)n; }
 
 void prof_begin(int st, cudaStream_t s) {
+    nvtxRangePushA(k_stage_names[st]);      // one NVTX range per stage (SURVEY section 5 "tracing"): visible in nsys / ncu --nvtx
     if (!g_prof_on) return;
     if (!g_prof_ev_ok) {
         for (int i = 0; i < ST_COUNT; ++i) { cudaEventCreate(&g_prof_ev[i][0]); cudaEventCreate(&g_prof_ev[i][1]); }
@@ -50,6 +52,7 @@ void prof_begin(int st, cudaStream_t s) {
     cudaEventRecord(g_prof_ev[st][0], s);
 }
 void prof_end(int st, cudaStream_t s) {
+    nvtxRangePop();
     if (!g_prof_on) return;
     cudaEventRecord(g_prof_ev[st][1], s);
     g_prof_used[st] = true;

@@ -99,6 +99,10 @@ def _load():
     for name in ("gsr_appearance_pack_weights", "gsr_appearance_colors_forward", "gsr_appearance_colors_backward",
                  "gsr_appearance_unpack_grads"):
         getattr(lib, name).restype = c_int
+    lib.gsr_gaussian_activations_forward.argtypes = [c_int] + [c_void_p] * 8
+    lib.gsr_gaussian_activations_forward.restype = c_int
+    lib.gsr_gaussian_activations_backward.argtypes = [c_int] + [c_void_p] * 11
+    lib.gsr_gaussian_activations_backward.restype = c_int
     lib.gsr_densification_stats.argtypes = [c_int] + [c_void_p] * 8
     lib.gsr_densification_stats.restype = c_int
     lib.gsr_profile_enable.argtypes = [c_int]

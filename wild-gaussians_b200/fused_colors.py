@@ -102,6 +102,46 @@ class _FusedColors(torch.autograd.Function):
         return (d_dc, d_rest, d_gemb, d_aemb.view_as(aemb), dW1, db1, dW2, db2, dW3, db3, d_means, None, None, None)
 
 
+class _FusedActivations(torch.autograd.Function):
+    """``GaussianModel.get_gaussians`` (method.py:1060-1086) without its features part: one kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, scales_raw, opacities_raw, rotations_raw, filter_3D):
+        dev = scales_raw.device
+        P = int(scales_raw.shape[0])
+        if not scales_raw.is_cuda:
+            raise RuntimeError("fused_activations needs CUDA tensors; there is no CPU path")
+        s, o, r, f = (_f32c(t.detach()) for t in (scales_raw, opacities_raw, rotations_raw, filter_3D))
+        if tuple(s.shape) != (P, 3) or o.numel() != P or tuple(r.shape) != (P, 4) or f.numel() != P:
+            raise RuntimeError("fused_activations: expected scales [P,3], opacities [P,1], rotations [P,4], filter_3D [P,1]")
+        with torch.cuda.device(dev):
+            so, oo, ro = torch.empty_like(s), torch.empty_like(o), torch.empty_like(r)
+            _C._check(_lib.gsr_gaussian_activations_forward(P, s.data_ptr(), o.data_ptr(), r.data_ptr(), f.data_ptr(), so.data_ptr(),
+                                                            oo.data_ptr(), ro.data_ptr(), _stream(dev)),
+                      "gsr_gaussian_activations_forward")
+        ctx.save_for_backward(s, o, r, f)
+        return so, oo, ro
+
+    @staticmethod
+    def backward(ctx, g_s, g_o, g_r):
+        s, o, r, f = ctx.saved_tensors
+        dev = s.device
+        P = int(s.shape[0])
+        with torch.cuda.device(dev):
+            g_s, g_o, g_r = (None if g is None else _f32c(g) for g in (g_s, g_o, g_r))
+            ds, do, dr = torch.empty_like(s), torch.empty_like(o), torch.empty_like(r)
+            ptr = lambda t: None if t is None else t.data_ptr()
+            _C._check(_lib.gsr_gaussian_activations_backward(P, s.data_ptr(), o.data_ptr(), r.data_ptr(), f.data_ptr(), ptr(g_s),
+                                                             ptr(g_o), ptr(g_r), ds.data_ptr(), do.data_ptr(), dr.data_ptr(),
+                                                             _stream(dev)), "gsr_gaussian_activations_backward")
+        return ds, do, dr, None
+
+
+def fused_activations(scales_raw, opacities_raw, rotations_raw, filter_3D):
+    """``(scales, opacities, rotations)`` as ``GaussianModel.get_gaussians`` returns them (method.py:1060-1086)."""
+    return _FusedActivations.apply(scales_raw, opacities_raw, rotations_raw, filter_3D)
+
+
 def fused_colors(features_dc, features_rest, embeddings, app_embedding, mlp, means3D, campos, active_sh_degree,
                  want_raw=True):
     """``(colors_raw [P,3] or None, colors_toned [P,3])``.  ``mlp`` is ``EmbeddingModel.mlp`` (nn.Sequential of

@@ -6,6 +6,7 @@ and for the statistics that consume its outputs. 
 
 rebinds ``model._render_internal`` to ``render_internal`` below, which returns the same dictionary but
 
+* evaluates the parameter activations + 3D filter (``get_gaussians``, method.py:1060-1086) with one kernel per direction;
 * evaluates the raw and the appearance-toned colours with ONE fused kernel per direction (``fused_colors``:
   tcgen05 MLP + SH evaluation, ``csrc/appearance.cu``) instead of ~60 PyTorch launches and several P x 128 / P x 48
   fp32 intermediates (method.py:1570-1598);
@@ -31,7 +32,7 @@ import numpy as np
 import torch
 
 from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
-from fused_colors import fused_colors
+from fused_colors import fused_activations, fused_colors
 
 _cam_cache: dict = {}
 _zero_cache: dict = {}
@@ -121,8 +122,9 @@ def render_internal(self, viewpoint_camera, config, *, kernel_size, scaling_modi
         debug=False, return_accumulation=True)
     rasterizer = GaussianRasterizer(raster_settings=settings)
 
-    g = self.get_gaussians()                        # activations + 3D filter (method.py:1060-1086)
-    means3D, opacity, scales, rotations = g["xyz"], g["opacities"], g["scales"], g["rotations"]
+    # activations + 3D filter (get_gaussians, method.py:1060-1086) in one kernel per direction
+    means3D = self.xyz
+    scales, opacity, rotations = fused_activations(self.scales, self.opacities, self.rotations, self.filter_3D)
     colors_raw, colors_toned = fused_colors(self.features_dc, self.features_rest, self.embeddings, embedding,
                                             self.appearance_mlp.mlp, means3D, cc["cam_center"], deg, want_raw=bool(return_raw))
     kw = dict(means3D=means3D, means2D=screenspace_points, opacities=opacity, scales=scales, rotations=rotations, shs=None,
