@@ -484,7 +484,7 @@ int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R_cap, size
     const uint32_t cap = (uint32_t)bs.units_cap;
     if (radix_num_passes(0, cell_bits) == 1) {
         // one pass sorted by the whole cell id: its digit totals ARE the items per cell
-        build_units_kernel<<<1, 1024, 0, s>>>(bs.cell_range, num_cells, bs.unit_base, radix_pass_totals(bs.radix_tmp, N1));
+        build_units_kernel<<<1, 1024, 0, s>>>(bs.cell_range, num_cells, bs.unit_base, radix_pass_totals(bs.radix_tmp, N1, 1));
         count_launches(1);
     } else {
         GSR_CUDA(cudaMemsetAsync(bs.cell_range, 0, (size_t)num_cells * sizeof(uint2), s));

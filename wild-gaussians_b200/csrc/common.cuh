@@ -127,7 +127,7 @@ int radix_sort_pairs(uint32_t* key_a, uint32_t* val_a, uint32_t* key_b, uint32_t
                      int begin_bit, int end_bit, uint32_t* tmp, cudaStream_t s, bool debug, const RadixAux* aux = nullptr,
                      const uint32_t* n_dev = nullptr, uint32_t* n_compact = nullptr);
 // digit totals (RADIX entries) left in `tmp` by the most recent pass of radix_sort_pairs over n items
-const uint32_t* radix_pass_totals(const uint32_t* tmp, size_t n);
+const uint32_t* radix_pass_totals(const uint32_t* tmp, size_t n, int passes);
 // exclusive scan of gathered counts: out[i] = sum_{j<i} counts[perm[j]], out[n] = total
 int scan_gathered(const uint32_t* counts, const uint32_t* perm, uint32_t* out, size_t n_cap,
                   uint32_t* tmp, cudaStream_t s, const uint32_t* n_dev = nullptr, uint32_t* total_out = nullptr);
