@@ -149,6 +149,7 @@ def test_fused_colors_against_torch_oracle(P, deg):
             assert worst[n] < 5e-2, (n, worst[n])
     for n, (c, r) in stats.items():
         assert c >= 0.99 and abs(r - 1.0) <= 0.03, (n, c, r)
+    assert fc.last_status_ok()                        # no barrier wait timed out inside the kernels
 
 
 def test_fused_colors_rejects_other_shapes_and_cpu():

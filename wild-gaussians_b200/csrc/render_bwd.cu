@@ -368,7 +368,6 @@ __global__ void __launch_bounds__(128) render_bwd_packed_kernel(const __grid_con
     __shared__ uint32_t s_id[PB];
     __shared__ __align__(16) float4 s_geo[PB];    // {x, y, hx, hy} for the per-warp culling
     __shared__ PairRec s_rec[PB];
-    __shared__ float s_thr[PB];                   // reject_threshold(opacity) of the staged Gaussians
     __shared__ __align__(16) float s_acc[PB][RB_ACC];
     __shared__ uint32_t s_max[WARPS];
 
@@ -453,7 +452,6 @@ __global__ void __launch_bounds__(128) render_bwd_packed_kernel(const __grid_con
                 rec.rg = make_float4(cr, cr, cg, cg);
                 rec.bk = make_float4(cb, cb, fabsf(c.w) * ddelx_dx, fabsf(c.w) * ddely_dy);
                 s_rec[tid] = rec;
-                s_thr[tid] = reject_threshold(c.w);
             }
             float4* a = reinterpret_cast<float4*>(s_acc[tid]);
             a[0] = a[1] = a[2] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -482,10 +480,6 @@ __global__ void __launch_bounds__(128) render_bwd_packed_kernel(const __grid_con
                 const float2 t3 = __fmul2_rn(dy, __fmul2_rn(hi2(ac), dy));
                 const float2 un = __fmul2_rn(dy, __fmul2_rn(lo2(bo), dx));       // -(B dx) dy
                 const float2 power = __ffma2_rn(__ffma2_rn(dx, t1, t3), mhalf, un);
-                // pairs that certainly fail alpha >= 1/255 (or power <= 0) are recognised before the expf
-                const float thr = s_thr[j];
-                if (!__any_sync(0xFFFFFFFFu, (pos < last_contributor[0] && !(power.x < thr) && !(power.x > 0.0f)) ||
-                                             (pos < last_contributor[1] && !(power.y < thr) && !(power.y > 0.0f)))) continue;
                 const float g0 = expf(power.x), g1 = expf(power.y);
                 const float2 oG = __fmul2_rn(hi2(bo), make_float2(g0, g1));
                 const float a0 = min(0.99f, oG.x), a1 = min(0.99f, oG.y);

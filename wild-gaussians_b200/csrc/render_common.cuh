@@ -63,13 +63,4 @@ __device__ __forceinline__ bool box_may_touch(const float4 g, const WarpBox& b) 
     return !(g.z < 0.f || g.x + g.z < b.x0 || g.x - g.z > b.x1 || g.y + g.w < b.y0 || g.y - g.w > b.y1);
 }
 
-// Largest `thr` such that power < thr implies min(0.99, o * expf(power)) < 1/255 FOR CERTAIN, i.e. a pair the reference
-// rejects at forward.cu:365: o e^power < 1/255  <=>  power < -ln(255 o); the margin (1e-5 relative + 1e-5 absolute)
-// is far above the rounding of logf / expf, so pairs within it still take the exact path and every decision is the
-// reference's.  NaN opacity gives NaN (no rejection).  Used per (warp, Gaussian) before the expensive part of a pair.
-__device__ __forceinline__ float reject_threshold(float o) {
-    const float L = logf(255.0f * o);
-    return -(L + fabsf(L) * 1e-5f + 1e-5f);
-}
-
 }  // namespace gsr

@@ -208,7 +208,7 @@ struct __align__(16) FwdPairRec {     // 80 bytes
     float4 ac;     // {conic.x, conic.x, conic.z, conic.z}
     float4 bo;     // {-conic.y, -conic.y, opacity, opacity}
     float4 rg;     // {r, r, g, g}
-    float4 bb;     // {b, b, thr, -}: power < thr  =>  opacity * exp(power) < 1/255 for certain (see reject_threshold)
+    float4 bb;     // {b, b, -, -}
 };
 
 __global__ void __launch_bounds__(128) render_fwd_packed_kernel(const __grid_constant__ RenderFwdParams p) {
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(128) render_fwd_packed_kernel(const __grid_con
                 rec.ac = make_float4(c.x, c.x, c.z, c.z);
                 rec.bo = make_float4(-c.y, -c.y, c.w, c.w);
                 rec.rg = make_float4(cr, cr, cg, cg);
-                rec.bb = make_float4(cb, cb, reject_threshold(c.w), 0.f);
+                rec.bb = make_float4(cb, cb, 0.f, 0.f);
                 s_rec[buf][tid] = rec;
             }
             if (r + 1 < rounds) {
@@ -316,10 +316,6 @@ __global__ void __launch_bounds__(128) render_fwd_packed_kernel(const __grid_con
                         const float2 t3 = __fmul2_rn(dy, __fmul2_rn(make_float2(ac.z, ac.w), dy));
                         const float2 un = __fmul2_rn(dy, __fmul2_rn(make_float2(bo.x, bo.y), dx));     // -(B dx) dy
                         const float2 power = __ffma2_rn(__ffma2_rn(dx, t1, t3), mhalf, un);
-                        // no pixel of the warp can reach alpha >= 1/255 (or has power <= 0): skip expf and the blend
-                        const float4 bb = R.bb;
-                        if (!__any_sync(0xFFFFFFFFu, (live0 && !(power.x < bb.z) && !(power.x > 0.0f)) ||
-                                                     (live1 && !(power.y < bb.z) && !(power.y > 0.0f)))) continue;
                         const float2 oG = __fmul2_rn(make_float2(bo.z, bo.w), make_float2(expf(power.x), expf(power.y)));
                         const float a0 = min(0.99f, oG.x), a1 = min(0.99f, oG.y);
                         const float2 test_T = __fmul2_rn(T, __fadd2_rn(one, make_float2(-a0, -a1)));
@@ -331,7 +327,7 @@ __global__ void __launch_bounds__(128) render_fwd_packed_kernel(const __grid_con
                         const bool upd0 = blend0 && !stop0, upd1 = blend1 && !stop1;
                         if (!__any_sync(0xFFFFFFFFu, upd0 || upd1)) continue;
                         const float2 alpha = make_float2(upd0 ? a0 : 0.f, upd1 ? a1 : 0.f);
-                        const float4 rg = R.rg;
+                        const float4 rg = R.rg, bb = R.bb;
                         C0 = __ffma2_rn(T, __fmul2_rn(alpha, make_float2(rg.x, rg.y)), C0);
                         C1 = __ffma2_rn(T, __fmul2_rn(alpha, make_float2(rg.z, rg.w)), C1);
                         C2 = __ffma2_rn(T, __fmul2_rn(alpha, make_float2(bb.x, bb.y)), C2);

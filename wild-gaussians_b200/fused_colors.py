@@ -22,6 +22,14 @@ from diff_gaussian_rasterization import _C
 _lib = _C._lib
 
 
+_last_status = {"fwd": None, "bwd": None}
+
+
+def last_status_ok() -> bool:
+    """False if a barrier wait inside the most recent fused colour kernels timed out (synchronises)."""
+    return all(t is None or int(t.item()) == 0 for t in _last_status.values())
+
+
 def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
@@ -62,6 +70,7 @@ class _FusedColors(torch.autograd.Function):
             a.colors_toned = toned.data_ptr()
             a.status = status.data_ptr()
             _C._check(_lib.gsr_appearance_colors_forward(byref(a), _stream(dev)), "gsr_appearance_colors_forward")
+            _last_status["fwd"] = status
         ctx.save_for_backward(fdc, frest, gemb, aemb, w1, means, cam, blob, status)
         ctx.deg, ctx.want_raw = int(active_sh_degree), bool(want_raw)
         if want_raw:
@@ -91,6 +100,7 @@ class _FusedColors(torch.autograd.Function):
             a.dL_dembeddings, a.dL_dmeans3D = d_gemb.data_ptr(), d_means.data_ptr()
             a.grad_pack, a.status = pack.data_ptr(), status.data_ptr()
             _C._check(_lib.gsr_appearance_colors_backward(byref(a), _stream(dev)), "gsr_appearance_colors_backward")
+            _last_status["bwd"] = status
             dW1, db1 = torch.empty((128, 59), **f32), torch.empty((128,), **f32)
             dW2, db2 = torch.empty((128, 128), **f32), torch.empty((128,), **f32)
             dW3, db3 = torch.empty((6, 128), **f32), torch.empty((6,), **f32)
@@ -155,6 +165,3 @@ def fused_colors(features_dc, features_rest, embeddings, app_embedding, mlp, mea
                                     int(active_sh_degree), bool(want_raw))
     return (raw if want_raw else None), toned
 
-
-def last_status_ok(status_tensor) -> bool:
-    return int(status_tensor.item()) == 0
