@@ -191,9 +191,10 @@ __device__ __forceinline__ void build_x_row(const ApParams& p, int row, bool val
 }
 
 // accumulator row (128 fp32 columns at TMEM column `col0`) -> ReLU -> bf16 -> chunks 0..15 of `hbuf`
-__device__ __forceinline__ void relu_epilogue(uint32_t tmem_row, uint32_t col0, uint8_t* hbuf, int t) {
+// (q0, q1): which of the four 32-column quarters this thread converts -- the backward kernel splits a row between two threads
+__device__ __forceinline__ void relu_epilogue(uint32_t tmem_row, uint32_t col0, uint8_t* hbuf, int t, int q0 = 0, int q1 = 4) {
 #pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
+    for (int q = q0; q < q1; ++q) {
         float v[32];
         tmem_ld32(tmem_row + col0 + 32 * q, v);
 #pragma unroll
@@ -207,9 +208,10 @@ __device__ __forceinline__ void relu_epilogue(uint32_t tmem_row, uint32_t col0, 
 }
 
 // accumulator row * (activation > 0) -> bf16 -> chunks 0..15 of `dzbuf` (ReLU backward; `hbuf` holds the activation)
-__device__ __forceinline__ void relu_bwd_epilogue(uint32_t tmem_row, uint32_t col0, const uint8_t* hbuf, uint8_t* dzbuf, int t) {
+__device__ __forceinline__ void relu_bwd_epilogue(uint32_t tmem_row, uint32_t col0, const uint8_t* hbuf, uint8_t* dzbuf, int t,
+                                                  int q0 = 0, int q1 = 4) {
 #pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
+    for (int q = q0; q < q1; ++q) {
         float v[32];
         tmem_ld32(tmem_row + col0 + 32 * q, v);
 #pragma unroll
@@ -250,31 +252,38 @@ __device__ __forceinline__ void write_const_chunks(uint8_t* hbuf, int t) {
 constexpr uint32_t FWD_SMEM = BLOB_BYTES + ACT_BYTES + REST_BYTES + 64;
 constexpr int FWD_TMEM_COLS = 256;     // scratch accumulator 128 + layer-3 accumulator 16, power of two
 
-__global__ void __launch_bounds__(AP_TILE) appearance_fwd_kernel(const __grid_constant__ ApParams p) {
+// 256 threads per CTA: thread (t, half) = row t, column half `half` of the two wide epilogues (the halves of a row sit in warps
+// w and w + 4, which address the same TMEM lanes); the input row and the colour epilogue are done by half 0.  With two
+// resident CTAs that is 16 warps per SM to hide the tcgen05.ld / shared-memory latency (ncu at 8 warps: 31 % issue-active,
+// long-scoreboard bound).
+constexpr int FWD_THREADS = 2 * AP_TILE;
+__global__ void __launch_bounds__(FWD_THREADS, 2) appearance_fwd_kernel(const __grid_constant__ ApParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_blob = smem;
     uint8_t* s_act = smem + BLOB_BYTES;
     float* s_rest = reinterpret_cast<float*>(smem + BLOB_BYTES + ACT_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BLOB_BYTES + ACT_BYTES + REST_BYTES);   // 0: mma, 1: loads, 2: weights
     __shared__ uint32_t s_tmem;
-    const int t = threadIdx.x, warp = t >> 5;
+    const int tid = threadIdx.x, t = tid & (AP_TILE - 1), half = tid >> 7, warp = tid >> 5;
+    const bool h0 = half == 0;
+    const int q0 = 2 * half, q1 = 2 * half + 2;
 
-    if (t == 0) {
+    if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
         mbar_init_fence();
     }
     if (warp == 0) tmem_alloc<FWD_TMEM_COLS>(&s_tmem);
-    write_const_chunks(s_act, t);
+    if (h0) write_const_chunks(s_act, t);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (t == 0) {
+    if (tid == 0) {
         mbar_expect_tx(&bars[2], BLOB_BYTES);
         bulk_g2s(s_blob, p.blob, BLOB_BYTES, &bars[2]);
     }
     const uint32_t tmem = s_tmem;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint8_t* w1p = s_blob;
     const uint8_t* w2p = s_blob + W1P_BYTES;
     const uint8_t* w3p = w2p + W2P_BYTES;
@@ -286,44 +295,45 @@ __global__ void __launch_bounds__(AP_TILE) appearance_fwd_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < p.num_tiles && !dead; tile += gridDim.x) {
         const int row0 = tile * AP_TILE, row = row0 + t;
         const int rows = min(AP_TILE, p.P - row0);
-        const bool valid = t < rows;
+        const bool valid = h0 && t < rows;
         const bool bulk = rows == AP_TILE;           // whole tiles: one 23 KB bulk copy; the ragged last tile: plain loads
         if (bulk) {
-            if (t == 0) {
+            if (tid == 0) {
                 mbar_expect_tx(&bars[1], REST_BYTES);
                 bulk_g2s(s_rest, p.rest + (size_t)row0 * AP_NREST, REST_BYTES, &bars[1]);
             }
         } else {
-            for (int i = t; i < rows * AP_NREST; i += AP_TILE) s_rest[i] = p.rest[(size_t)row0 * AP_NREST + i];
+            for (int i = tid; i < rows * AP_NREST; i += FWD_THREADS) s_rest[i] = p.rest[(size_t)row0 * AP_NREST + i];
         }
         RowIn in;
-        build_x_row(p, row, valid, t, s_act, in);
+        in.dc[0] = in.dc[1] = in.dc[2] = 0.f; in.dir = {0.f, 0.f, 1.f}; in.inv_norm = 0.f;
+        if (h0) build_x_row(p, row, valid, t, s_act, in);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (t == 0) {
+        if (tid == 0) {
             fence_after_sync();
 #pragma unroll
             for (int k = 0; k < AP_K1 / 16; ++k) mma_bf16(tmem, desc_k(s_act, k, AP_TILE), desc_k(w1p, k, AP_H), ID_N128, k > 0);
             commit(&bars[0]);
         }
         AP_WAIT(&bars[0], ph_mma);
-        relu_epilogue(tmem_row, 0, s_act, t);
+        relu_epilogue(tmem_row, 0, s_act, t, q0, q1);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (t == 0) {
+        if (tid == 0) {
             fence_after_sync();
 #pragma unroll
             for (int k = 0; k < AP_K2 / 16; ++k) mma_bf16(tmem, desc_k(s_act, k, AP_TILE), desc_k(w2p, k, AP_H), ID_N128, k > 0);
             commit(&bars[0]);
         }
         AP_WAIT(&bars[0], ph_mma);
-        relu_epilogue(tmem_row, 0, s_act, t);
+        relu_epilogue(tmem_row, 0, s_act, t, q0, q1);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (t == 0) {
+        if (tid == 0) {
             fence_after_sync();
 #pragma unroll
             for (int k = 0; k < AP_K2 / 16; ++k) mma_bf16(tmem + 128, desc_k(s_act, k, AP_TILE), desc_k(w3p, k, AP_N3), ID_N16, k > 0);
@@ -331,7 +341,7 @@ __global__ void __launch_bounds__(AP_TILE) appearance_fwd_kernel(const __grid_co
         }
         AP_WAIT(&bars[0], ph_mma);
         float o[16];
-        tmem_ld16(tmem_row + 128, o);
+        if (h0) tmem_ld16(tmem_row + 128, o);
         if (bulk) { if (!mbar_wait(&bars[1], ph_ld)) { if (p.status) atomicExch(p.status, 1); dead = true; } ph_ld ^= 1u; }
         if (valid) {
             float b[16];
@@ -378,7 +388,12 @@ constexpr uint32_t BWD_SMEM = BLOB_BYTES + BX_BYTES + 2 * ACT_BYTES + BDZ_BYTES 
 // TMEM columns: scratch 0..127 | layer-3 128..143 | dX 160..191 | acc dW2p 192..335 | acc dW1p 336..367 | acc dW3pT 368..383
 constexpr uint32_t TC_D3 = 128, TC_DX = 160, TC_W2 = 192, TC_W1 = 336, TC_W3 = 368;
 
-__global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_constant__ ApParams p) {
+// 256 threads: thread (t, half) -- row t of the tile, column half `half` of the wide epilogues.  The two halves of a row sit in
+// warps w and w + 4, which address the same 32 TMEM lanes (lane base = 32 * (warp % 4)); eight warps per SM instead of four
+// hide the tcgen05.ld / shared-memory latency of the four 128-column epilogues.  Per-row work that cannot be split (input row,
+// colour stage, dX) is done by half 0.
+constexpr int BWD_THREADS = 2 * AP_TILE;
+__global__ void __launch_bounds__(BWD_THREADS) appearance_bwd_kernel(const __grid_constant__ ApParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_blob = smem;
     uint8_t* s_x = s_blob + BLOB_BYTES;
@@ -390,27 +405,31 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_rest) + REST_BYTES);
     float* s_db3 = reinterpret_cast<float*>(bars + 4);       // [8]
     __shared__ uint32_t s_tmem;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int tid = threadIdx.x, t = tid & (AP_TILE - 1), half = tid >> 7, warp = tid >> 5, lane = tid & 31;
+    const bool h0 = half == 0;
+    const int q0 = 2 * half, q1 = 2 * half + 2;
 
-    if (t == 0) {
+    if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
         mbar_init_fence();
     }
-    if (t < 8) s_db3[t] = 0.f;
+    if (tid < 8) s_db3[tid] = 0.f;
     if (warp == 0) tmem_alloc<512>(&s_tmem);
-    write_const_chunks(s_h1, t);
-    write_const_chunks(s_h2, t);
-    st_chunk(s_do, 1, t, make_uint4(0u, 0u, 0u, 0u));
+    if (h0) {
+        write_const_chunks(s_h1, t);
+        write_const_chunks(s_h2, t);
+        st_chunk(s_do, 1, t, make_uint4(0u, 0u, 0u, 0u));
+    }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    if (t == 0) {
+    if (tid == 0) {
         mbar_expect_tx(&bars[2], BLOB_BYTES);
         bulk_g2s(s_blob, p.blob, BLOB_BYTES, &bars[2]);
     }
     const uint32_t tmem = s_tmem;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint8_t* w1p = s_blob;
     const uint8_t* w2p = s_blob + W1P_BYTES;
     const uint8_t* w3p = w2p + W2P_BYTES;
@@ -425,46 +444,47 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < p.num_tiles && !dead; tile += gridDim.x, ++iter) {
         const int row0 = tile * AP_TILE, row = row0 + t;
         const int rows = min(AP_TILE, p.P - row0);
-        const bool valid = t < rows;
+        const bool valid = h0 && t < rows;
         const bool bulk = rows == AP_TILE;
         const bool acc = iter > 0;
         if (bulk) {
-            if (t == 0) {
+            if (tid == 0) {
                 mbar_expect_tx(&bars[1], REST_BYTES);
                 bulk_g2s(s_rest, p.rest + (size_t)row0 * AP_NREST, REST_BYTES, &bars[1]);
             }
         } else {
-            for (int i = t; i < rows * AP_NREST; i += AP_TILE) s_rest[i] = p.rest[(size_t)row0 * AP_NREST + i];
+            for (int i = tid; i < rows * AP_NREST; i += BWD_THREADS) s_rest[i] = p.rest[(size_t)row0 * AP_NREST + i];
         }
         RowIn in;
-        build_x_row(p, row, valid, t, s_x, in);
+        in.dc[0] = in.dc[1] = in.dc[2] = 0.f; in.dir = {0.f, 0.f, 1.f}; in.inv_norm = 0.f;
+        if (h0) build_x_row(p, row, valid, t, s_x, in);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
         // ---- forward recompute -----------------------------------------------------------------------------------
-        if (t == 0) {
+        if (tid == 0) {
             fence_after_sync();
 #pragma unroll
             for (int k = 0; k < AP_K1 / 16; ++k) mma_bf16(tmem, desc_k(s_x, k, AP_TILE), desc_k(w1p, k, AP_H), ID_F128, k > 0);
             commit(&bars[0]);
         }
         AP_WAIT(&bars[0], ph_mma);
-        relu_epilogue(tmem_row, 0, s_h1, t);
+        relu_epilogue(tmem_row, 0, s_h1, t, q0, q1);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (t == 0) {
+        if (tid == 0) {
             fence_after_sync();
 #pragma unroll
             for (int k = 0; k < AP_K2 / 16; ++k) mma_bf16(tmem, desc_k(s_h1, k, AP_TILE), desc_k(w2p, k, AP_H), ID_F128, k > 0);
             commit(&bars[0]);
         }
         AP_WAIT(&bars[0], ph_mma);
-        relu_epilogue(tmem_row, 0, s_h2, t);
+        relu_epilogue(tmem_row, 0, s_h2, t, q0, q1);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (t == 0) {
+        if (tid == 0) {
             fence_after_sync();
 #pragma unroll
             for (int k = 0; k < AP_K2 / 16; ++k) mma_bf16(tmem + TC_D3, desc_k(s_h2, k, AP_TILE), desc_k(w3p, k, AP_N3), ID_F16, k > 0);
@@ -472,7 +492,7 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
         }
         AP_WAIT(&bars[0], ph_mma);
         float o[16];
-        tmem_ld16(tmem_row + TC_D3, o);
+        if (h0) tmem_ld16(tmem_row + TC_D3, o);
         if (bulk) { if (!mbar_wait(&bars[1], ph_ld)) { if (p.status) atomicExch(p.status, 1); dead = true; } ph_ld ^= 1u; }
 
         // ---- colour stage backward: dL/d{raw, toned} -> dL/d features, dL/d(offset, mul), dL/d mean ----------------
@@ -528,21 +548,23 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
             p.g_means[(size_t)row * 3 + 2] = dm.z;
         }
         // dO (bf16) -> shared memory; bias gradient of the last layer = column sums of dO (fp32, warp shuffles)
-        st_chunk(s_do, 0, t, make_uint4(pack_bf16(dOut[0], dOut[1]), pack_bf16(dOut[2], dOut[3]), pack_bf16(dOut[4], dOut[5]), 0u));
+        if (h0) {
+            st_chunk(s_do, 0, t, make_uint4(pack_bf16(dOut[0], dOut[1]), pack_bf16(dOut[2], dOut[3]), pack_bf16(dOut[4], dOut[5]), 0u));
 #pragma unroll
-        for (int j = 0; j < AP_NOUT; ++j) {
-            float v = dOut[j];
+            for (int j = 0; j < AP_NOUT; ++j) {
+                float v = dOut[j];
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, s);
-            if (lane == 0) atomicAdd(&s_db3[j], v);
+                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, s);
+                if (lane == 0) atomicAdd(&s_db3[j], v);
+            }
         }
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
         // coalesced copy-out of the tile's features_rest gradients (they replaced the features in s_rest)
-        for (int i = t; i < rows * AP_NREST; i += AP_TILE) p.g_rest[(size_t)row0 * AP_NREST + i] = s_rest[i];
+        for (int i = tid; i < rows * AP_NREST; i += BWD_THREADS) p.g_rest[(size_t)row0 * AP_NREST + i] = s_rest[i];
         // ---- layer 3 backward --------------------------------------------------------------------------------------
-        if (t == 0) {
+        if (tid == 0) {
             fence_after_sync();
             // dH2 = dO . W3           A: dO K-major (K = 16 outputs), B: W3p as MN-major (N = 128 inputs)
             mma_bf16(tmem, desc_k(s_do, 0, AP_TILE), desc_mn(w3p, 0, AP_N3), ID_DG128, false);
@@ -553,12 +575,12 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
             commit(&bars[0]);
         }
         AP_WAIT(&bars[0], ph_mma);
-        relu_bwd_epilogue(tmem_row, 0, s_h2, s_dz, t);
+        relu_bwd_epilogue(tmem_row, 0, s_h2, s_dz, t, q0, q1);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
         // ---- layer 2 backward --------------------------------------------------------------------------------------
-        if (t == 0) {
+        if (tid == 0) {
             fence_after_sync();
             // dW2p[128 out][144 in] += dZ2^T . H1p   (column 128 of H1p is the constant one: bias gradient)
 #pragma unroll
@@ -570,12 +592,12 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
             commit(&bars[0]);
         }
         AP_WAIT(&bars[0], ph_mma);
-        relu_bwd_epilogue(tmem_row, 0, s_h1, s_dz, t);
+        relu_bwd_epilogue(tmem_row, 0, s_h1, s_dz, t, q0, q1);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
         // ---- layer 1 backward --------------------------------------------------------------------------------------
-        if (t == 0) {
+        if (tid == 0) {
             fence_after_sync();
 #pragma unroll
             for (int k = 0; k < AP_TILE / 16; ++k)
@@ -585,7 +607,7 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
             commit(&bars[0]);
         }
         AP_WAIT(&bars[0], ph_mma);
-        {
+        if (h0) {
             float dx[32];
             tmem_ld32(tmem_row + TC_DX, dx);
             if (valid) {
@@ -606,7 +628,7 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
     if (iter > 0 && !dead) {
         float* g = p.g_pack;
         auto flush = [&](uint32_t col0, int ncols, size_t base, int ld) {
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
+            for (int c0 = 16 * half; c0 < ncols; c0 += 32) {      // the two halves of a row take alternate 16-column groups
                 float v[16];
                 tmem_ld16(tmem_row + col0 + c0, v);
                 float* dst = g + base + (size_t)t * ld + c0;
@@ -619,7 +641,7 @@ __global__ void __launch_bounds__(AP_TILE) appearance_bwd_kernel(const __grid_co
         flush(TC_W2, AP_K2, GW2P, AP_K2);
         flush(TC_W1, AP_K1, GW1P, AP_K1);
         flush(TC_W3, AP_N3, GW3P, AP_N3);
-        if (t < AP_NOUT) atomicAdd(g + GB3 + t, s_db3[t]);
+        if (tid < AP_NOUT) atomicAdd(g + GB3 + tid, s_db3[tid]);
     }
     fence_before_sync();
     __syncthreads();
@@ -698,7 +720,7 @@ int gsr_appearance_colors_forward(const GsrAppearanceArgs* a, void* stream) {
     const ApParams p = ap_params(a);
     GSR_CUDA(cudaFuncSetAttribute(appearance_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
     const int grid = min(p.num_tiles, 2 * ap_num_sms());      // persistent: two resident CTAs per SM
-    appearance_fwd_kernel<<<grid, AP_TILE, FWD_SMEM, (cudaStream_t)stream>>>(p);
+    appearance_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(p);
     count_launches(1);
     GSR_CUDA(cudaGetLastError());
     return 0;
@@ -712,7 +734,7 @@ int gsr_appearance_colors_backward(const GsrAppearanceArgs* a, void* stream) {
     GSR_CUDA(cudaMemsetAsync(a->grad_pack, 0, GPACK_FLOATS * sizeof(float), s));
     GSR_CUDA(cudaFuncSetAttribute(appearance_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
     const int grid = min(p.num_tiles, ap_num_sms());          // persistent: one CTA per SM (187 KB of shared memory)
-    appearance_bwd_kernel<<<grid, AP_TILE, BWD_SMEM, s>>>(p);
+    appearance_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(p);
     count_launches(1);
     GSR_CUDA(cudaGetLastError());
     return 0;

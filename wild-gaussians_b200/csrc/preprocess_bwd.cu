@@ -209,9 +209,10 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
 
         // (3) cov2D -> Sigma and -> the projection rows.  G = dL_da t0 t0^T + dL_db/2 (t0 t1^T + t1 t0^T) + dL_dc t1 t1^T
         //     is dL/dSigma (rank 2); dL/dt0 = 2 dL_da Sigma t0 + dL_db Sigma t1, dL/dt1 = 2 dL_dc Sigma t1 + dL_db Sigma t0.
-        auto sym = [&](const V3& v) -> V3 {       // Sigma v, Sigma given by its upper triangle
-            return {cov3D[0] * v.x + cov3D[1] * v.y + cov3D[2] * v.z, cov3D[1] * v.x + cov3D[3] * v.y + cov3D[4] * v.z,
-                    cov3D[2] * v.x + cov3D[4] * v.y + cov3D[5] * v.z};
+        const Mat3& S3 = e.Vrk;                   // Sigma (symmetric), already in registers
+        auto sym = [&](const V3& v) -> V3 {       // Sigma v
+            return {S3.m[0][0] * v.x + S3.m[1][0] * v.y + S3.m[2][0] * v.z, S3.m[0][1] * v.x + S3.m[1][1] * v.y + S3.m[2][1] * v.z,
+                    S3.m[0][2] * v.x + S3.m[1][2] * v.y + S3.m[2][2] * v.z};
         };
         const V3 u0 = sym(t0), u1 = sym(t1);
         const V3 g0 = (2.0f * dL_da) * u0 + dL_db * u1;

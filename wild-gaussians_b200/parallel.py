@@ -106,21 +106,32 @@ class _PeerState:
     def __init__(self, P, H, W, device, group):
         import torch.distributed._symmetric_memory as symm_mem
         g = group if group is not None else dist.group.WORLD
-        self.accum = symm_mem.empty(P * 12 + 64, dtype=torch.float32, device=device)
-        self.accum.zero_()
-        self.accum_hdl = symm_mem.rendezvous(self.accum, g)
-        self.image = symm_mem.empty(4 * H * W, dtype=torch.float32, device=device)
-        self.image_hdl = symm_mem.rendezvous(self.image, g)
-        self.mc = 0
+        # two accumulators, used alternately (same argument as for the images below: with several backward passes per
+        # step -- wild-gaussians composites twice -- a rank's reductions of pass k+1 must not land in a peer's accumulator
+        # while that peer is still consuming pass k; pass k+2 lies behind pass k+1's barrier)
+        self.accums = [symm_mem.empty(P * 12 + 64, dtype=torch.float32, device=device) for _ in range(2)]
+        for t in self.accums:
+            t.zero_()
+        self.accum_hdls = [symm_mem.rendezvous(t, g) for t in self.accums]
+        self.bwd = 0
+        # two images, used alternately: a rank may start storing frame k+1 into its peers while a slower peer is still
+        # copying frame k out of its own buffer (forward-only loops have no other barrier in between); it cannot reach
+        # frame k+2 before that peer has passed frame k+1's barrier, i.e. finished the copy of frame k
+        self.images = [symm_mem.empty(4 * H * W, dtype=torch.float32, device=device) for _ in range(2)]
+        self.image_hdls = [symm_mem.rendezvous(t, g) for t in self.images]
+        self.frame = 0
+        self.mcs = [0, 0]
         if _PEER_MODE >= 2:
-            try:
-                self.mc = int(self.accum_hdl.multicast_ptr or 0)
-            except Exception:
-                self.mc = 0
-        assert self.accum.data_ptr() % 256 == 0 and all(int(x) % 256 == 0 for x in self.accum_hdl.buffer_ptrs)
-        self.world = self.accum_hdl.world_size
-        # every rank's accumulator is zero before anyone adds into it
-        self.accum_hdl.barrier(channel=0)
+            for i, h in enumerate(self.accum_hdls):
+                try:
+                    self.mcs[i] = int(h.multicast_ptr or 0)
+                except Exception:
+                    self.mcs[i] = 0
+        for t, h in zip(self.accums, self.accum_hdls):
+            assert t.data_ptr() % 256 == 0 and all(int(x) % 256 == 0 for x in h.buffer_ptrs)
+        self.world = self.accum_hdls[0].world_size
+        # every rank's accumulators are zero before anyone adds into them
+        self.accum_hdls[0].barrier(channel=0)
 
 
 def _peers(P, H, W, device, group):
@@ -153,10 +164,12 @@ def sharded_forward(fwd_args, bands, group=None):
     shard = tuple(bands[rank])
     st = _peers(P, H, W, means3D.device, group)
     if st is not None:
+        image, hdl = st.images[st.frame], st.image_hdls[st.frame]
+        st.frame ^= 1
         R, _none, radii, geom, binning, img = _C.rasterize_gaussians_shard(
-            shard, *fwd_args, peer_images=(st.image_hdl.buffer_ptrs_dev, st.world))
-        st.image_hdl.barrier(channel=0)             # every band has landed in every rank's image
-        full = st.image.view(4, H, W).clone()       # the symmetric buffer is overwritten by the next forward
+            shard, *fwd_args, peer_images=(hdl.buffer_ptrs_dev, st.world))
+        hdl.barrier(channel=0)                      # every band has landed in every rank's image
+        full = image.view(4, H, W).clone()          # the symmetric buffer is overwritten two forwards later
         return full, R, radii, geom, binning, img
     R, color, radii, geom, binning, img = _C.rasterize_gaussians_shard(shard, *fwd_args)
     offset = (128 - img.data_ptr()) % 128
@@ -175,10 +188,11 @@ def reduced_partials(bwd_args, P: int, device, group=None, shard=None) -> torch.
     if st is not None:
         # the accumulators of all ranks are zero here: cleared by the previous step's chain-rule kernel (or at creation),
         # and the forward's image barrier lies between that kernel and this one on every rank
-        _C.rasterize_gaussians_backward_partials_peers(st.accum, st.accum_hdl.buffer_ptrs_dev, st.world, st.mc, *bwd_args,
-                                                       shard=shard)
-        st.accum_hdl.barrier(channel=1)          # all contributions have landed everywhere
-        return st.accum
+        accum, hdl, mc = st.accums[st.bwd], st.accum_hdls[st.bwd], st.mcs[st.bwd]
+        st.bwd ^= 1
+        _C.rasterize_gaussians_backward_partials_peers(accum, hdl.buffer_ptrs_dev, st.world, mc, *bwd_args, shard=shard)
+        hdl.barrier(channel=1)                   # all contributions have landed everywhere
+        return accum
     accum = _C.rasterize_gaussians_backward_partials(*bwd_args, shard=shard)
     reduce_partials(accum[: P * 12], group)
     return accum
