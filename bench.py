@@ -659,6 +659,10 @@ def main():
 
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a.config, kw)
+        # BASELINE.json config 1 (10k Gaussians, 256x256, SH degree 0: "the reference's own CPU-runnable case") in full, not sampled
+        kw1 = dict(synthetic.CONFIGS["C1"]); kw1["seed"] = 0
+        c1 = cpu_baseline("C1", kw1, frac=1.0)
+        line["cpu_baseline"]["config1"] = {"value": c1["value"], "unit": c1["unit"], "cores": c1["cores"], "sample": c1["sample"]}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
