@@ -137,9 +137,17 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
     float o_rot[4] = {0.f, 0.f, 0.f, 0.f};
     bool sh_written = false;
 
+    // A visible Gaussian that no pixel blended (occluded, or alpha < 1/255 everywhere: most of a dense scene) has an
+    // all-zero row of sums: every gradient of it is zero, so its inputs are not even read.
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
     if (rendered) {
         const float4* acc = reinterpret_cast<const float4*>(p.accum + (size_t)idx * 12);
-        const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2];
+        a0 = acc[0]; a1 = acc[1]; a2 = acc[2];
+    }
+    const bool touched = (a0.x != 0.f) | (a0.y != 0.f) | (a0.z != 0.f) | (a0.w != 0.f) | (a1.x != 0.f) | (a1.y != 0.f) |
+                         (a1.z != 0.f) | (a1.w != 0.f) | (a2.x != 0.f) | (a2.y != 0.f);
+
+    if (rendered && touched) {
         o_mean2D[0] = a0.x; o_mean2D[1] = a0.y; o_mean2D[2] = a0.z;
         o_conic[0] = a0.w; o_conic[1] = a1.x; o_conic[3] = a1.y;
         float dL_dopacity = a1.z;
