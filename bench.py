@@ -917,6 +917,25 @@ def full_train_step(kw, dev, steps, impl="ours"):
         wf.enable(model)
         res["ours_fused_caller_ms"] = time_steps(lambda: wh.train_step(model, cfg, cam, G1, G2), steps, 3, dev, 1)
         wf.disable(model)
+        # the optimizer step of the iteration (method.py:2019) on the optimizer the unmodified
+        # `_setup_optimizers` (method.py:1029-1053) builds: PyTorch's Adam (foreach path) vs the same object adopted by
+        # fused_adam (one kernel, csrc/adam.cu); gradients = those of the last train step, kept alive across the timed steps
+        try:
+            import fused_adam
+            model.spatial_lr_scale.fill_(1.7)
+            model._setup_optimizers()
+            wh.train_step(model, cfg, cam, G1, G2)
+            n_el = sum(p.numel() for g_ in model.optimizer.param_groups for p in g_["params"] if p.grad is not None)
+            opt = {"elements": n_el, "alg_bytes": 28 * n_el,
+                   "what": "model.optimizer.step() (Adam, 10 parameter groups incl. the appearance MLP), CUDA events, ms"}
+            opt["torch_adam_ms"] = time_steps(model.optimizer.step, steps, 3, dev, 1)
+            fused_adam.adopt(model.optimizer)
+            opt["fused_adam_ms"] = time_steps(model.optimizer.step, steps, 3, dev, 1)
+            opt["fused_gbs"] = opt["alg_bytes"] / (opt["fused_adam_ms"] * 1e-3) / 1e9
+            opt["fused_frac_of_hbm_peak"] = opt["fused_gbs"] / peaks()[0]
+            res["optimizer_step"] = opt
+        except Exception as e:          # reporting only
+            res["optimizer_step"] = {"unavailable": f"{type(e).__name__}: {e}"}
     finally:
         wh.use_backend(m, ours.GaussianRasterizer, ours.GaussianRasterizationSettings)
         ours._C.set_geometry_cache(False)

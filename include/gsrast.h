@@ -297,6 +297,39 @@ int gsr_gaussian_activations_backward(int P, const float* scales_raw, const floa
 int gsr_densification_stats(int P, const int* radii, const float* viewspace_grad, float* max_radii2D, float* xyz_grad,
                             float* xyz_gradient_accum_abs, float* xyz_gradient_accum_abs_max, float* denom, void* stream);
 
+/* -- optimizer step (optional entry point) ------------------------------------------------------------------
+ * One launch replacing `self.model.optimizer.step()` (wildgaussians/method.py:2019) of the Adam optimizer built at
+ * method.py:1033-1049 (lr per group, eps = 1e-15, weight_decay on the appearance-embedding table only; amsgrad /
+ * maximize off).  The algorithm lives in the reference's third-party dependency PyTorch (optim/adam.py,
+ * _multi_tensor_adam); this entry point performs the same fp32 operations per element, all tensors in one pass.
+ * `step` is the 1-based step count of the tensor AFTER this update (PyTorch increments state["step"] first); lr / step
+ * may differ per segment.  All pointers are device pointers to fp32 arrays of `n` elements; `grad` is only written when
+ * zero_grads != 0 (it is then left all-zero, the in-place counterpart of zero_grad()).                                  */
+#define GSR_ADAM_MAX_SEGMENTS 32
+typedef struct GsrAdamSegment {
+    float* param;
+    float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    long long n;
+    long long step;
+    double lr;
+    double weight_decay;
+} GsrAdamSegment;
+int gsr_adam_step(const GsrAdamSegment* segments, int num_segments, double beta1, double beta2, double eps, int zero_grads,
+                  void* stream);
+
+/* -- 3D filter sizes over all training cameras (optional entry point) -----------------------------------------
+ * Replaces GaussianModel.compute_3D_filter (wildgaussians/method.py:1140-1190): per Gaussian the smallest camera-space depth
+ * over the cameras that see it (depth > 0.2 and projection inside the image enlarged by 15 %), Gaussians no camera sees get
+ * the largest such depth; filter_3D = distance / focal_length * sqrt(0.2).  `cameras` is a device array of num_cameras
+ * records of 20 floats: R[9] (row-major, the matrix method.py:1165 multiplies with: xyz @ R + T), T[3], fx, fy, W/2, H/2,
+ * -0.15 W, 1.15 W, -0.15 H, 1.15 H; `focal_length` = the largest fx (method.py:1178-1179).  `scratch`: device memory of
+ * gsr_filter3d_scratch_bytes(P) bytes, 16-byte aligned.  filter_3D: [P] (the reference stores it as [P,1]).               */
+size_t gsr_filter3d_scratch_bytes(int P);
+int gsr_compute_3d_filter(int P, const float* xyz, int num_cameras, const float* cameras, float focal_length,
+                          float* filter_3D, void* scratch, void* stream);
+
 /* Optional per-stage device timing (cudaEvents on the caller's stream around each stage of the
  * next forward / backward calls).  The caller synchronises the stream, then reads the stage times of
  * the most recent calls in milliseconds (-1 for stages that did not run).  Not thread-safe.        */

@@ -60,6 +60,14 @@ class GsrAppearanceArgs(Structure):
     ]
 
 
+class GsrAdamSegment(Structure):      # include/gsrast.h
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("n", ctypes.c_longlong), ("step", ctypes.c_longlong), ("lr", ctypes.c_double), ("weight_decay", ctypes.c_double)]
+
+
+ADAM_MAX_SEGMENTS = 32
+
+
 class GsrStats(Structure):
     _fields_ = [("num_rendered", c_int), ("num_visible", c_int), ("num_tiles", c_int), ("num_coarse", c_int)]
 
@@ -105,6 +113,12 @@ def _load():
     lib.gsr_gaussian_activations_backward.restype = c_int
     lib.gsr_densification_stats.argtypes = [c_int] + [c_void_p] * 8
     lib.gsr_densification_stats.restype = c_int
+    lib.gsr_adam_step.argtypes = [POINTER(GsrAdamSegment), c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_int, c_void_p]
+    lib.gsr_adam_step.restype = c_int
+    lib.gsr_filter3d_scratch_bytes.argtypes = [c_int]
+    lib.gsr_filter3d_scratch_bytes.restype = c_size_t
+    lib.gsr_compute_3d_filter.argtypes = [c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]
+    lib.gsr_compute_3d_filter.restype = c_int
     lib.gsr_profile_enable.argtypes = [c_int]
     lib.gsr_profile_enable.restype = None
     lib.gsr_profile_stage_count.restype = c_int

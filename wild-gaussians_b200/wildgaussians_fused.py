@@ -166,12 +166,66 @@ def densification_stats(model, viewspace_point_tensor, radii) -> None:
             torch.cuda.current_stream(dev).cuda_stream), "gsr_densification_stats")
 
 
-def enable(model):
-    """Route this model's ``_render_internal`` through the fused path (instance attribute; the class is untouched)."""
+def camera_table(cameras) -> tuple:
+    """The per-camera constants of ``compute_3D_filter`` (method.py:1147-1181) for all cameras as one [C, 20] float32 array
+    (layout: include/gsrast.h, gsr_compute_3d_filter) and the focal length of the highest-resolution camera (:1178-1179).
+    Built with the reference's own statements (numpy 4x4 inverse, transposed rotation) in one pass on the host."""
+    rows, focal = [], 0.0
+    for camera in cameras:
+        assert camera.image_sizes is not None, "Camera image size is not set"
+        fx, fy, _, _ = camera.intrinsics
+        width, height = camera.image_sizes
+        pose = np.copy(camera.poses)
+        pose = np.concatenate([pose, np.array([[0, 0, 0, 1]], dtype=pose.dtype)], axis=0)
+        pose = np.linalg.inv(pose)
+        R = np.transpose(pose[:3, :3]).astype(np.float32)
+        T = pose[:3, 3].astype(np.float32)
+        f32 = np.float32
+        rows.append(np.concatenate([R.reshape(-1), T, np.array(
+            [f32(fx), f32(fy), f32(width / 2.0), f32(height / 2.0), f32(-0.15 * width), f32(width * 1.15), f32(-0.15 * height),
+             f32(1.15 * height)], dtype=np.float32)]))
+        if focal < fx:
+            focal = fx
+    table = np.stack(rows).astype(np.float32) if rows else np.zeros((0, 20), dtype=np.float32)
+    return table, float(focal)
+
+
+def compute_3D_filter(model, cameras) -> None:
+    """``GaussianModel.compute_3D_filter`` (method.py:1140-1190) in two kernels over all cameras (csrc/filter3d.cu) instead of
+    ~20 PyTorch launches + 2 H2D copies + 2 host synchronisations PER CAMERA; registers the same ``filter_3D`` buffer."""
+    xyz = model.xyz
+    if not (xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous()):
+        return type(model).compute_3D_filter(model, cameras)
+    table, focal = camera_table(cameras)
+    if table.shape[0] == 0 or not focal > 0:
+        return type(model).compute_3D_filter(model, cameras)
+    dev, P = xyz.device, int(xyz.shape[0])
+    with torch.no_grad(), torch.cuda.device(dev):
+        cams = torch.from_numpy(table).to(dev)
+        scratch = torch.empty((_C._lib.gsr_filter3d_scratch_bytes(P) + 15) // 16 * 4, dtype=torch.float32, device=dev)
+        out = torch.empty((P,), dtype=torch.float32, device=dev)
+        _C._check(_C._lib.gsr_compute_3d_filter(P, xyz.data_ptr(), int(table.shape[0]), cams.data_ptr(), focal, out.data_ptr(),
+                                                scratch.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                  "gsr_compute_3d_filter")
+        filter_3D = out.to(dtype=model.filter_3D.dtype, device=model.filter_3D.device)
+        del model.filter_3D
+        model.register_buffer("filter_3D", filter_3D[..., None])
+
+
+def enable(model, optimizer: bool = True):
+    """Route this model's ``_render_internal`` and ``compute_3D_filter`` through the fused paths (instance attributes; the
+    class is untouched) and, with ``optimizer``, turn its Adam into the single-kernel ``fused_adam.FusedAdam`` in place."""
     model._render_internal = types.MethodType(render_internal, model)
+    model.compute_3D_filter = types.MethodType(compute_3D_filter, model)
+    if optimizer and type(getattr(model, "optimizer", None)) is torch.optim.Adam:
+        import fused_adam
+        fused_adam.adopt(model.optimizer)
     return model
 
 
 def disable(model):
     model.__dict__.pop("_render_internal", None)
+    model.__dict__.pop("compute_3D_filter", None)
+    if type(getattr(model, "optimizer", None)).__name__ == "FusedAdam":
+        model.optimizer.__class__ = torch.optim.Adam
     return model
