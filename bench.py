@@ -530,9 +530,11 @@ def main():
                 torch.cuda.empty_cache()
                 s_step, _, _ = make_e2e_step(api["GaussianRasterizer"], scene, dev, api["GaussianRasterizationSettings"])
                 s_ms = time_steps(s_step, max(3, a.steps // 2), 3, dev, 1)
-                line["e2e"] = {"value": P * N / (e_ms * 1e-3), "unit": line["unit"], "ms_per_step": e_ms,
-                               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step_serial_copies": s_ms,
-                               "note": E2E_NOTE}
+                best = min(e_ms, s_ms)      # the reference gets the better of the two forms (its 15 ms of compute hide little)
+                line["e2e"] = {"value": P * N / (best * 1e-3), "unit": line["unit"], "ms_per_step": best,
+                               "ms_per_step_pipelined": e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                               "ms_per_step_serial_copies": s_ms,
+                               "note": E2E_NOTE + ".  Reference arm: value = the FASTER of its pipelined and serial forms"}
             if a.config == "C3" and not a.no_other_configs:
                 def factory(dd):
                     st = {}

@@ -330,6 +330,14 @@ size_t gsr_filter3d_scratch_bytes(int P);
 int gsr_compute_3d_filter(int P, const float* xyz, int num_cameras, const float* cameras, float focal_length,
                           float* filter_3D, void* scratch, void* stream);
 
+/* -- initial scales from the point cloud (optional entry point) -------------------------------------------
+ * Replaces distCUDA2 of the reference's simple-knn submodule (spatial.cu:15-26 -> SimpleKNN::knn, simple_knn.cu:185-220;
+ * called once at method.py:1001): mean_dist2[i] = mean of the squared distances from point i to its 3 nearest OTHER points
+ * (fp32, the reference's expression and summation order; exact search, so the values are the reference's).
+ * points: [P,3] fp32 on the device; scratch: gsr_knn_scratch_bytes(P) bytes of device memory, 256-byte aligned.           */
+size_t gsr_knn_scratch_bytes(int P);
+int gsr_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* scratch, void* stream);
+
 /* Optional per-stage device timing (cudaEvents on the caller's stream around each stage of the
  * next forward / backward calls).  The caller synchronises the stream, then reads the stage times of
  * the most recent calls in milliseconds (-1 for stages that did not run).  Not thread-safe.        */

@@ -69,9 +69,6 @@ def test_kernel_matches_golden_and_oracle(name):
 
 @pytest.mark.gpu
 def test_kernel_matches_unmodified_method_on_the_device_and_unseen_gaussians():
-    import sys
-    sys.path.insert(0, GOLD)
-    import make_golden_filter3d as mg
     import wg_harness as wh
     import wildgaussians_fused as wf
     m, Config = wh.import_method()
@@ -85,9 +82,14 @@ def test_kernel_matches_unmodified_method_on_the_device_and_unseen_gaussians():
     g = torch.Generator().manual_seed(9)
     with torch.no_grad():
         pts = torch.randn(P, 3, generator=g) * 2.5
-        pts[:5000] += 500.0                       # far outside every frustum: exercised `distance[~valid] = max`
+        pts[:5000, 2] = -60.0 - pts[:5000, 2].abs()      # behind every camera below: exercises `distance[~valid] = max`
         model.xyz.copy_(pts)
-    cams = mg.make_cameras(40, 21)
+    cams = []
+    for k in range(40):                                  # cameras at z = -8 .. -6 looking along +z, slightly shifted
+        c2w = np.concatenate([np.eye(3, dtype=np.float32), np.array([[0.05 * k - 1.0], [0.3 * (k % 3)], [-8.0 + 0.05 * k]], dtype=np.float32)], axis=1)
+        W, H = 640 + 8 * k, 480 + 4 * k
+        cams.append(types.SimpleNamespace(poses=c2w, image_sizes=np.array([W, H], dtype=np.int32),
+                                          intrinsics=np.array([420.0 + 3 * k, 425.0 + 3 * k, W / 2.0, H / 2.0], dtype=np.float32)))
     model.compute_3D_filter(cams)                 # the reference's own statements, on the GPU
     want = model.filter_3D.detach().cpu().numpy().reshape(-1)
     wf.enable(model)

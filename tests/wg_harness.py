@@ -39,6 +39,13 @@ def import_method():
     root = reference_root()
     if root is None:
         return None, None
+    for p in (os.path.join(ROOT, "wild-gaussians_b200"), root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:                                        # this repo's drop-in for the reference's simple-knn submodule
+        import simple_knn._C  # noqa: F401
+    except Exception:
+        pass
     for name in ("omegaconf", "plyfile", "simple_knn", "simple_knn._C"):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules["omegaconf"].OmegaConf = getattr(sys.modules["omegaconf"], "OmegaConf", object)

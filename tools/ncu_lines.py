@@ -10,6 +10,13 @@ rep, kre, cubin = sys.argv[1:4]
 min_pct = float(sys.argv[4]) if len(sys.argv) > 4 else 0.5
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
+if not rows:
+    print("no kernel matching", kre, "in", rep); sys.exit(1)
+# several captured launches of the same kernel: keep the first table only
+for _i in range(1, len(rows)):
+    if rows[_i] and rows[_i][0] == "Kernel Name":
+        rows = rows[:_i]
+        break
 kname = rows[0][1]
 hdr = rows[1]
 ie, isamp, isrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")

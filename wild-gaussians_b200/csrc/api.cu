@@ -504,10 +504,11 @@ int gsr_backward_finalize(const GsrBackwardArgs* a, void* stream) {
     if (rc) return rc;
     GSR_STAGE(s, a->debug != 0, "preprocess_bwd_kernel");
     prof_end(ST_PREPROCESS_BWD, s);
-    // leave the accumulator zeroed for the next backward pass (stream-ordered fill AFTER its only reader): a caller that
-    // keeps the buffer passes accum_is_zero = 1 next time, and the tile-row sharded path needs no fill + barrier in front
-    // of its peer reductions.  (Clearing the consumed rows inside the kernel was measured 3.5x slower for the kernel.)
-    GSR_CUDA(cudaMemsetAsync(accum_of(a), 0, (size_t)a->P * sizeof(BwdAccum), s));
+    // leave the accumulator zeroed for the next backward pass: a caller that keeps the buffer passes accum_is_zero = 1 next
+    // time, and the tile-row sharded path needs no fill + barrier in front of its peer reductions.  The kernel clears the
+    // rows it found non-zero itself (only the Gaussians some pixel blended: 10-20 % of a dense scene; clearing ALL rows in
+    // the kernel was measured 3.5x slower than the kernel + a memset); GSR_ACCUM_CLEAR=0 keeps the stream-ordered memset.
+    if (!preprocess_bwd_clears_accum()) GSR_CUDA(cudaMemsetAsync(accum_of(a), 0, (size_t)a->P * sizeof(BwdAccum), s));
     return 0;
 }
 

@@ -155,6 +155,7 @@ int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinSta
                       const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s,
                       const PeerAccum* peer = nullptr);
 int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum* accum, cudaStream_t s);
+bool preprocess_bwd_clears_accum();   // GSR_ACCUM_CLEAR (default 1): the chain-rule kernel zeroes the rows it consumed
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);
 

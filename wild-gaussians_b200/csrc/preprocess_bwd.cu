@@ -33,6 +33,7 @@ struct PreBwdParams {
     const float* campos;
     const float4* rec;
     const float* accum;     // [P][12]
+    float* accum_clear;     // the same array when the kernel is to zero the rows it consumed (see launch_preprocess_bwd), else NULL
     float* dL_dmean2D;      // [P,3]
     float* dL_dconic;       // [P,4] or NULL
     float* dL_dopacity;     // [P]
@@ -146,6 +147,13 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
     }
     const bool touched = (a0.x != 0.f) | (a0.y != 0.f) | (a0.z != 0.f) | (a0.w != 0.f) | (a1.x != 0.f) | (a1.y != 0.f) |
                          (a1.z != 0.f) | (a1.w != 0.f) | (a2.x != 0.f) | (a2.y != 0.f);
+    // keep the accumulator all-zero between passes by clearing just the rows that were non-zero (typically 10-20 % of the
+    // Gaussians) instead of a 48 B x P memset after the kernel
+    if (touched && p.accum_clear != nullptr) {
+        float4* w = reinterpret_cast<float4*>(p.accum_clear + (size_t)idx * 12);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        w[0] = z; w[1] = z; w[2] = z;
+    }
 
     if (rendered && touched) {
         o_mean2D[0] = a0.x; o_mean2D[1] = a0.y; o_mean2D[2] = a0.z;
@@ -331,6 +339,16 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
     if (p.dL_drot) reinterpret_cast<float4*>(p.dL_drot)[i] = make_float4(o_rot[0], o_rot[1], o_rot[2], o_rot[3]);
 }
 
+// 1: the kernel zeroes the accumulator rows it consumed (the caller then skips its memset)
+bool preprocess_bwd_clears_accum() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GSR_ACCUM_CLEAR");
+        v = e ? atoi(e) : 1;
+    }
+    return v != 0;
+}
+
 int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum* accum, cudaStream_t s) {
     PreBwdParams p;
     p.P = a.P; p.D = a.D; p.M = a.M;
@@ -342,6 +360,7 @@ int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum
     p.scales = a.scales; p.rotations = a.rotations; p.cov3D_precomp = a.cov3D_precomp;
     p.view = a.viewmatrix; p.proj = a.projmatrix; p.campos = a.campos;
     p.rec = g.rec; p.accum = reinterpret_cast<const float*>(accum);
+    p.accum_clear = preprocess_bwd_clears_accum() ? reinterpret_cast<float*>(accum) : nullptr;
     p.dL_dmean2D = a.dL_dmean2D; p.dL_dconic = a.dL_dconic; p.dL_dopacity = a.dL_dopacity;
     p.dL_dcolor = a.dL_dcolor; p.dL_dmean3D = a.dL_dmean3D; p.dL_dcov3D = a.dL_dcov3D;
     p.dL_dsh = a.dL_dsh; p.dL_dscale = a.dL_dscale; p.dL_drot = a.dL_drot;

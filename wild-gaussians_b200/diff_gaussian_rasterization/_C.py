@@ -119,6 +119,10 @@ def _load():
     lib.gsr_filter3d_scratch_bytes.restype = c_size_t
     lib.gsr_compute_3d_filter.argtypes = [c_int, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]
     lib.gsr_compute_3d_filter.restype = c_int
+    lib.gsr_knn_scratch_bytes.argtypes = [c_int]
+    lib.gsr_knn_scratch_bytes.restype = c_size_t
+    lib.gsr_knn_mean_dist2.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.gsr_knn_mean_dist2.restype = c_int
     lib.gsr_profile_enable.argtypes = [c_int]
     lib.gsr_profile_enable.restype = None
     lib.gsr_profile_stage_count.restype = c_int
