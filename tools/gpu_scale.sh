@@ -19,6 +19,6 @@ except Exception as e:
     print("  ${name} FAILED", e)
 PY
 }
-for n in "$@"; do
+if [ "${BASH_SOURCE[0]}" = "$0" ]; then for n in "$@"; do
   run c3_${n}gpu $n GSR_DUMMY=0 -- --no-train-step --no-other-configs --no-cpu-baseline
-done
+done; fi

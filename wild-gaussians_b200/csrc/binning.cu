@@ -230,6 +230,48 @@ __global__ void __launch_bounds__(1024) tile_offsets_kernel(const uint32_t* __re
     if (threadIdx.x == 0) tile_start[num_tiles] = s_carry[0];
 }
 
+// Multi-CTA form: CTA b owns tiles [1024 b, 1024 (b + 1)); it publishes its block total (flag | sum in one 64-bit word) and
+// adds up the totals of the CTAs before it (at most a few dozen, all resident: <= 120 CTAs are launched, lower indices are
+// dispatched first), so the dependent global-load chain of the counts is paid once, in parallel, instead of once per 1024
+// tiles.  `block_sums` must be zero on entry.
+__global__ void __launch_bounds__(1024) tile_offsets_lookback_kernel(const uint32_t* __restrict__ Pm, const uint32_t* __restrict__ row_total,
+                                                                     const uint32_t* __restrict__ unit_base, uint32_t cap, int cells_x,
+                                                                     int grid_x, int num_tiles, uint32_t* __restrict__ tile_start,
+                                                                     uint2* __restrict__ ranges, unsigned long long* block_sums) {
+    __shared__ uint32_t s_wa[32], s_wb[32], s_carry[2];
+    __shared__ uint32_t s_prev;
+    if (threadIdx.x < 2) s_carry[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_prev = 0;
+    __syncthreads();
+    const int t = (int)blockIdx.x * 1024 + (int)threadIdx.x;
+    uint32_t cnt = 0, dummy = 0, local, ex_dummy;
+    if (t < num_tiles) {
+        const int tx = t % grid_x, ty = t / grid_x;
+        const uint32_t c = (uint32_t)((ty / CELL) * cells_x + tx / CELL), lt = (uint32_t)((ty % CELL) * CELL + tx % CELL);
+        cnt = prefix_at(Pm, row_total, cap, lt, unit_base[c + 1]) - prefix_at(Pm, row_total, cap, lt, unit_base[c]);
+    }
+    const uint32_t mine = cnt;
+    block_scan2_1024(cnt, dummy, s_wa, s_wb, s_carry, local, ex_dummy);      // s_carry[0] = this CTA's total afterwards
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicExch(&block_sums[blockIdx.x], (1ull << 32) | (unsigned long long)s_carry[0]);
+    }
+    // totals of the CTAs in front: thread j < blockIdx.x waits for CTA j's word
+    if (threadIdx.x < blockIdx.x) {
+        unsigned long long w;
+        unsigned spins = 0;       // bounded: a scheduling surprise must not hang the GPU (the ranges would be wrong instead)
+        do { w = atomicAdd(&block_sums[threadIdx.x], 0ull); } while ((w >> 32) == 0ull && ++spins < (1u << 26));
+        atomicAdd(&s_prev, (uint32_t)w);
+    }
+    __syncthreads();
+    const uint32_t start = s_prev + local;
+    if (t < num_tiles) {
+        tile_start[t] = start;
+        ranges[t] = mine ? make_uint2(start, start + mine) : make_uint2(0u, 0u);
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) tile_start[num_tiles] = s_prev + s_carry[0];
+}
+
 // ---- level 2c: scatter ------------------------------------------------------------------------------
 // One warp per unit.  Lane l owns the running output position of local tiles l and l + 32 (column l & 7, rows
 // l >> 3 and 4 + (l >> 3) of the cell).  The unit's coarse items are walked IN ORDER, 32 at a time: every lane
@@ -503,7 +545,15 @@ int run_tile_binning(const GeomState& g, int P, int W, int H, size_t R_cap, size
     // exact output positions
     rc = row_scan_u32(bs.M, CELL_TILES, cap, bs.row_total, s);
     if (rc) return rc;
-    tile_offsets_kernel<<<1, 1024, 0, s>>>(bs.M, bs.row_total, bs.unit_base, cap, cells_x, gx, num_tiles, bs.tile_start, ranges);
+    const int off_ctas = (num_tiles + 1023) / 1024;
+    if (off_ctas > 1 && off_ctas <= 120) {
+        unsigned long long* block_sums = reinterpret_cast<unsigned long long*>(bs.tile_count);     // [T+1] words, 256-B aligned, otherwise unused
+        GSR_CUDA(cudaMemsetAsync(block_sums, 0, (size_t)off_ctas * sizeof(unsigned long long), s));
+        tile_offsets_lookback_kernel<<<off_ctas, 1024, 0, s>>>(bs.M, bs.row_total, bs.unit_base, cap, cells_x, gx, num_tiles,
+                                                               bs.tile_start, ranges, block_sums);
+    } else {
+        tile_offsets_kernel<<<1, 1024, 0, s>>>(bs.M, bs.row_total, bs.unit_base, cap, cells_x, gx, num_tiles, bs.tile_start, ranges);
+    }
     count_launches(1);
     GSR_STAGE(s, debug, "tile_offsets_kernel");
     prof_end(ST_TILE_OFFSETS, s);

@@ -122,6 +122,59 @@ __global__ void __launch_bounds__(1024) radix_rowscan_kernel(uint32_t* __restric
     if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
 }
 
+// The same scan for LONG rows (the count matrix of the tile binning: 64 rows of ~20 k columns): K chunks of 1024 columns per
+// round share the two barriers of a round (warp w combines the warp totals of chunk w), so a row costs cols / (K * 1024)
+// dependent rounds instead of cols / 1024; loads and stores stay coalesced.
+template <int K>
+__global__ void __launch_bounds__(1024) rowscan_wide_kernel(uint32_t* __restrict__ hist, uint32_t cols, uint32_t* __restrict__ total) {
+    __shared__ uint32_t s_warp[K][32];
+    __shared__ uint32_t s_carry;
+    uint32_t* row = hist + (size_t)blockIdx.x * cols;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < cols; base += K * 1024) {
+        uint32_t v[K], x[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t i = base + k * 1024 + threadIdx.x;
+            v[k] = i < cols ? row[i] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            x[k] = v[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x[k], o);
+                if (lane >= o) x[k] += y;
+            }
+            if (lane == 31) s_warp[k][warp] = x[k];
+        }
+        __syncthreads();
+        if (warp < K) {
+            uint32_t w = s_warp[warp][lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[warp][lane] = w;      // inclusive over the warps of chunk `warp`
+        }
+        __syncthreads();
+        uint32_t off = s_carry;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t i = base + k * 1024 + threadIdx.x;
+            if (i < cols) row[i] = off + (warp == 0 ? 0u : s_warp[k][warp - 1]) + x[k] - v[k];
+            off += s_warp[k][31];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = off;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
+}
+
 template <bool DROP, bool AUX>
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                    const uint32_t* __restrict__ vals_in,
@@ -487,7 +540,8 @@ const uint32_t* radix_pass_totals(const uint32_t* tmp, size_t n, int passes) {
 
 int row_scan_u32(uint32_t* m, int rows, size_t cols, uint32_t* total, cudaStream_t s) {
     if (rows <= 0 || cols == 0) return 0;
-    radix_rowscan_kernel<<<rows, 1024, 0, s>>>(m, (uint32_t)cols, total);
+    if (cols > 4096) rowscan_wide_kernel<8><<<rows, 1024, 0, s>>>(m, (uint32_t)cols, total);
+    else radix_rowscan_kernel<<<rows, 1024, 0, s>>>(m, (uint32_t)cols, total);
     count_launches(1);
     GSR_CUDA(cudaGetLastError());
     return 0;
