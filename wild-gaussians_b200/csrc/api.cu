@@ -4,6 +4,7 @@
 // rasterizer_impl.h:21-73.  All work is enqueued on the caller's stream; the only host
 // synchronisation is the read-back of the instance count R (the reference blocks on the same
 // value, rasterizer_impl.cu:283-284).
+#include <atomic>
 #include "common.cuh"
 
 #include <cstdarg>
@@ -38,9 +39,9 @@ static bool g_prof_on = false;
 static cudaEvent_t g_prof_ev[ST_COUNT][2];
 static bool g_prof_ev_ok = false;
 static bool g_prof_used[ST_COUNT];
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};
 
-void count_launches(int n) { g_launches += (unsigned long long)n; }
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void prof_begin(int st, cudaStream_t s) {
     nvtxRangePushA(k_stage_names[st]);      // one NVTX range per stage (SURVEY section 5 "tracing"): visible in nsys / ncu --nvtx
@@ -192,7 +193,7 @@ int gsr_profile_read(float* ms, int n) {
     }
     return 0;
 }
-unsigned long long gsr_launch_count(void) { return g_launches; }
+unsigned long long gsr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* gsr_last_error(void) { return g_err; }
 
 int gsr_forward_sizes(int P, int M, int W, int H, size_t* geom_bytes, size_t* img_bytes) {
@@ -248,12 +249,25 @@ static int geometry_stage(const GsrForwardArgs* a, const GeomState& g, int ty0, 
     return 0;
 }
 
-// synchronising read-back of the counters through a small pinned buffer (a pageable destination makes the copies
-// synchronous staging copies); one buffer per host thread, never freed
+// synchronising read-back of the counters.  NOT a cudaMemcpy: a device-to-host copy would queue on the D2H copy engine behind
+// whatever another stream is reading back at that moment (a host-buffer pipeline reads 229 MB of gradients per step: the
+// 32-byte copy then waits ~4 ms and the forward with it).  A one-warp kernel stores the eight counters straight into mapped
+// pinned host memory instead (SM stores over PCIe, no copy engine); one buffer per host thread, never freed.
+__global__ void counters_to_host_kernel(const int32_t* __restrict__ counters, volatile int32_t* __restrict__ host) {
+    if (threadIdx.x < 8) host[threadIdx.x] = counters[threadIdx.x];
+    __threadfence_system();
+}
+
 static int read_counters(const GeomState& g, cudaStream_t s, int32_t out[8]) {
     static thread_local int32_t* h_counts = nullptr;
-    if (!h_counts) GSR_CUDA(cudaHostAlloc((void**)&h_counts, 8 * sizeof(int32_t), cudaHostAllocDefault));
-    GSR_CUDA(cudaMemcpyAsync(h_counts, g.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    static thread_local int32_t* d_alias = nullptr;
+    if (!h_counts) {
+        GSR_CUDA(cudaHostAlloc((void**)&h_counts, 8 * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+        GSR_CUDA(cudaHostGetDevicePointer((void**)&d_alias, h_counts, 0));
+    }
+    counters_to_host_kernel<<<1, 32, 0, s>>>(g.counters, d_alias);
+    count_launches(1);
+    GSR_CUDA(cudaGetLastError());
     GSR_CUDA(cudaStreamSynchronize(s));
     memcpy(out, h_counts, 8 * sizeof(int32_t));
     return 0;
