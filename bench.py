@@ -12,7 +12,8 @@ Rank 0 prints ONE JSON line:
   value / ms_per_step   Gaussians*pixels/s = P*N / t_step, device-timed (CUDA events), max over ranks
   e2e                   the same metric through the public Python API (GaussianRasterizer + autograd) with every
                         tensor argument copied from pinned host memory each step and the image + all gradients read
-                        back to the host, copies inside the timed region
+                        back to the host, copies inside the timed region; value = consecutive steps software-pipelined
+                        (same harness for both arms), plus the one-step-in-flight and serial-copy forms
   roofline              dominant kernel: algorithmic bytes / its event-timed duration vs MEASURED_PEAKS.json
   roofline_path         SURVEY.md 8(d) whole-path formula (B_fwd + B_bwd) / (t_fwd + t_bwd)
   stages                per-stage device times (events inside libgsrast, averaged over K profiled steps run right
@@ -45,7 +46,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import synthetic  # noqa: E402
 
 FALLBACK_HBM_GBS = 6650.0
-E2E_NOTE = ("value / ms_per_step: public API (GaussianRasterizer + autograd) on pinned HOST buffers, every step copies all of its "
+E2E_NOTE = ("value / ms_per_step = the FASTEST of the forms below (both arms).  ms_per_step_pipelined: public API (GaussianRasterizer + autograd) on pinned HOST buffers, every step copies all of its "
             "inputs host->device and its image + all gradients device->host inside the timed region; steps are software-pipelined "
             "(<= 3 in flight: step i's read-back overlaps step i+1's uploads on the other PCIe direction; the closing event waits "
             "for the last read-back) -- the SAME harness times both arms.  ms_per_step_one_step_in_flight (ours): copies "
@@ -773,7 +774,8 @@ def main():
         del p_step, p_fin
         torch.cuda.empty_cache()
         e_ms = time_steps(e_step, max(3, a.steps // 2), 3, dev, world)
-        line["e2e"] = {"value": P * N / (p_ms * 1e-3), "unit": line["unit"], "ms_per_step": p_ms,
+        best = min(p_ms, e_ms)          # every arm reports the faster of its forms (the reference arm does the same)
+        line["e2e"] = {"value": P * N / (best * 1e-3), "unit": line["unit"], "ms_per_step": best, "ms_per_step_pipelined": p_ms,
                        "ms_per_step_one_step_in_flight": e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
         if world == 1:
             s_step, _, _ = make_e2e_step(GaussianRasterizer, scene, dev, GaussianRasterizationSettings, None)

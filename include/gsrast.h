@@ -212,6 +212,20 @@ int    gsr_backward_finalize(const GsrBackwardArgs* args, void* stream);
 int    gsr_backward_partials_peers(const GsrBackwardArgs* args, const void* const* peer_accum_dev, int n_peers,
                                    void* multicast_accum, void* stream);
 
+/* "Pull" form of the multi-GPU reduction (GSR_PEER_REDUCE=3): no remote atomics at all.  gsr_backward_partials_marked adds
+ * this rank's band into ITS OWN accumulator (args->accum_scratch) and sets touched[i] = 1 for every Gaussian i it added to
+ * (one byte per Gaussian, all-zero on entry).  After a barrier, gsr_backward_finalize_pull forms each Gaussian's complete
+ * sums as own row + the rows the other ranks marked, read through their peer-mapped accumulators in rank order 0..n-1
+ * (the same order on every rank: the resulting gradients are bit-identical across ranks), and runs the chain rule.
+ * peer_accum_dev / peer_touched_dev: DEVICE arrays of n_peers device pointers (entry `self` = this rank's own buffers).
+ * The buffers of THIS pass must stay untouched until every rank has finished reading them, i.e. until the barrier of the
+ * next pass: keep two sets and pass the previous pass's set as clear_accum / clear_touched (may be NULL) -- its marked
+ * rows and marks are zeroed by this call.                                                                             */
+int    gsr_backward_partials_marked(const GsrBackwardArgs* args, unsigned char* touched, void* stream);
+int    gsr_backward_finalize_pull(const GsrBackwardArgs* args, const void* const* peer_accum_dev,
+                                  const void* const* peer_touched_dev, int n_peers, int self, void* clear_accum,
+                                  unsigned char* clear_touched, void* stream);
+
 /* -- markVisible (rasterizer_impl.cu:54-66,141-153): present[i] = (view*p).z > 0.2 ------- */
 int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present, void* stream);

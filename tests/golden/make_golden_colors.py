@@ -19,15 +19,20 @@ REF = "/root/reference"
 
 
 def import_reference():
+    for p in (os.path.join(ROOT, "wild-gaussians_b200"), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:                                        # this repo's drop-in for the reference's simple-knn submodule
+        import simple_knn._C  # noqa: F401
+    except Exception:
+        pass
     for name in ("omegaconf", "plyfile", "simple_knn", "simple_knn._C"):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules["omegaconf"].OmegaConf = object
     sys.modules["plyfile"].PlyData = object
     sys.modules["plyfile"].PlyElement = object
-    sys.modules["simple_knn._C"].distCUDA2 = None
-    for p in (os.path.join(ROOT, "wild-gaussians_b200"), REF):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+    if not hasattr(sys.modules["simple_knn._C"], "distCUDA2"):
+        sys.modules["simple_knn._C"].distCUDA2 = None
     import wildgaussians.method as m
     from wildgaussians.config import Config
     return m, Config

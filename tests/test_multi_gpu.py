@@ -59,10 +59,11 @@ def _worker(rank, world, port, q, peer_mode=0):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("peer_mode", [0, 1, 2], ids=["nccl_allreduce", "peer_red", "multicast_red"])
+@pytest.mark.parametrize("peer_mode", [0, 1, 2, 3], ids=["nccl_allreduce", "peer_red", "multicast_red", "pull"])
 def test_sharded_equals_single_gpu(peer_mode):
     """peer_mode 0: NCCL all-reduce of the partial gradients; 1 / 2: the reduction fused into the backward composite
-    through peer pointers / the NVSwitch multicast address (symmetric memory)."""
+    through peer pointers / the NVSwitch multicast address (symmetric memory); 3: local sums + marks, every rank pulls the
+    marked rows of the others (no remote atomics)."""
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs >= 2 GPUs")

@@ -465,7 +465,7 @@ static BwdAccum* accum_of(const GsrBackwardArgs* a) {
     return accum;
 }
 
-static int backward_partials_impl(const GsrBackwardArgs* a, void* stream, const PeerAccum* peer) {
+static int backward_partials_impl(const GsrBackwardArgs* a, void* stream, const PeerAccum* peer, unsigned char* touched = nullptr) {
     int rc = check_bwd_args(a, true, false);
     if (rc || a->P == 0) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -484,7 +484,7 @@ static int backward_partials_impl(const GsrBackwardArgs* a, void* stream, const 
     const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
     if (a->R > 0) {
         prof_begin(ST_RENDER_BWD, s);
-        rc = launch_render_bwd(*a, g, b, im, colors, accum, ty0, ty1, s, peer);
+        rc = launch_render_bwd(*a, g, b, im, colors, accum, ty0, ty1, s, peer, touched);
         if (rc) return rc;
         GSR_STAGE(s, dbg, "render_bwd_kernel");
         prof_end(ST_RENDER_BWD, s);
@@ -505,6 +505,36 @@ int gsr_backward_partials_peers(const GsrBackwardArgs* a, const void* const* pee
     peer.n_peers = multicast_accum ? 0 : n_peers;
     peer.multicast = multicast_accum;
     return backward_partials_impl(a, stream, &peer);
+}
+
+int gsr_backward_partials_marked(const GsrBackwardArgs* a, unsigned char* touched, void* stream) {
+    if (!touched) { set_error("touched is NULL"); return GSR_E_INVALID; }
+    if (a && !a->accum_is_zero) { set_error("gsr_backward_partials_marked needs accum_is_zero (the pull-mode buffers are kept zero)"); return GSR_E_INVALID; }
+    return backward_partials_impl(a, stream, nullptr, touched);
+}
+
+int gsr_backward_finalize_pull(const GsrBackwardArgs* a, const void* const* peer_accum_dev, const void* const* peer_touched_dev,
+                               int n_peers, int self, void* clear_accum, unsigned char* clear_touched, void* stream) {
+    int rc = check_bwd_args(a, false, true);
+    if (rc || a->P == 0) return rc;
+    if (!peer_accum_dev || !peer_touched_dev || n_peers <= 0 || self < 0 || self >= n_peers || ((clear_accum == nullptr) != (clear_touched == nullptr))) {
+        set_error("gsr_backward_finalize_pull: bad peer arguments");
+        return GSR_E_INVALID;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    GeomState g;
+    carve_geom((char*)a->geom_buffer, a->P, a->M, &g);
+    PullPeers pull;
+    pull.accums = reinterpret_cast<const float* const*>(peer_accum_dev);
+    pull.touched = reinterpret_cast<const unsigned char* const*>(peer_touched_dev);
+    pull.n_peers = n_peers; pull.self = self;
+    pull.clear_accum = reinterpret_cast<float*>(clear_accum); pull.clear_touched = clear_touched;
+    prof_begin(ST_PREPROCESS_BWD, s);
+    rc = launch_preprocess_bwd(*a, g, accum_of(a), s, &pull);
+    if (rc) return rc;
+    GSR_STAGE(s, a->debug != 0, "preprocess_bwd_kernel");
+    prof_end(ST_PREPROCESS_BWD, s);
+    return 0;     // nothing is cleared here: this pass's buffers are zeroed by the NEXT pass's call (see gsrast.h)
 }
 
 int gsr_backward_finalize(const GsrBackwardArgs* a, void* stream) {

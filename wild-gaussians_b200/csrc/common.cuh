@@ -153,8 +153,17 @@ struct PeerAccum {
 };
 int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinState& b, const ImgState& im,
                       const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s,
-                      const PeerAccum* peer = nullptr);
-int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum* accum, cudaStream_t s);
+                      const PeerAccum* peer = nullptr, unsigned char* touched = nullptr);
+// pull-mode reduction (render_bwd marks, preprocess_bwd gathers the marked rows of the other ranks): see gsrast.h
+struct PullPeers {
+    const float* const* accums;          // device array [n_peers] of accumulator pointers (peer-mapped)
+    const unsigned char* const* touched; // device array [n_peers] of mark arrays
+    int n_peers, self;
+    float* clear_accum;                  // previous pass's own accumulator / marks to zero, or NULL
+    unsigned char* clear_touched;
+};
+int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum* accum, cudaStream_t s,
+                          const PullPeers* pull = nullptr);
 bool preprocess_bwd_clears_accum();   // GSR_ACCUM_CLEAR (default 1): the chain-rule kernel zeroes the rows it consumed
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t s);

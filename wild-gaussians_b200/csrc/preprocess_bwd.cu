@@ -34,6 +34,12 @@ struct PreBwdParams {
     const float4* rec;
     const float* accum;     // [P][12]
     float* accum_clear;     // the same array when the kernel is to zero the rows it consumed (see launch_preprocess_bwd), else NULL
+    // pull-mode multi-GPU reduction (gsrast.h, gsr_backward_finalize_pull): complete sums = rows of all ranks in rank order
+    const float* const* pull_accums;          // device array [pull_n] of the ranks' accumulators, or NULL
+    const unsigned char* const* pull_touched; // device array [pull_n] of the ranks' mark arrays
+    int pull_n, pull_self;
+    float* pull_clear_accum;                  // previous pass's own accumulator: rows marked in pull_clear_touched are zeroed
+    unsigned char* pull_clear_touched;
     float* dL_dmean2D;      // [P,3]
     float* dL_dconic;       // [P,4] or NULL
     float* dL_dopacity;     // [P]
@@ -141,7 +147,28 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
     // A visible Gaussian that no pixel blended (occluded, or alpha < 1/255 everywhere: most of a dense scene) has an
     // all-zero row of sums: every gradient of it is zero, so its inputs are not even read.
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
-    if (rendered) {
+    if (p.pull_accums != nullptr) {
+        // rows of all ranks, added in rank order (identical on every rank -> bit-identical gradients everywhere); a rank that
+        // did not mark the Gaussian contributes an all-zero row, which is skipped (x + 0 = x) without reading it
+        if (rendered) {
+            for (int r = 0; r < p.pull_n; ++r) {
+                if (r != p.pull_self && p.pull_touched[r][idx] == 0) continue;
+                const float4* acc = reinterpret_cast<const float4*>((r == p.pull_self ? p.accum : p.pull_accums[r]) + (size_t)idx * 12);
+                const float4 b0 = acc[0], b1 = acc[1], b2 = acc[2];
+                a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+                a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+                a2.x += b2.x; a2.y += b2.y;
+            }
+        }
+        // the PREVIOUS pass's buffers are no longer read by anyone (every rank passed this pass's barrier after finishing that
+        // pass's chain rule): zero the rows this rank marked then, and the marks
+        if (p.pull_clear_touched != nullptr && p.pull_clear_touched[idx] != 0) {
+            float4* w = reinterpret_cast<float4*>(p.pull_clear_accum + (size_t)idx * 12);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            w[0] = z; w[1] = z; w[2] = z;
+            p.pull_clear_touched[idx] = 0;
+        }
+    } else if (rendered) {
         const float4* acc = reinterpret_cast<const float4*>(p.accum + (size_t)idx * 12);
         a0 = acc[0]; a1 = acc[1]; a2 = acc[2];
     }
@@ -349,7 +376,7 @@ bool preprocess_bwd_clears_accum() {
     return v != 0;
 }
 
-int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum* accum, cudaStream_t s) {
+int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum* accum, cudaStream_t s, const PullPeers* pull) {
     PreBwdParams p;
     p.P = a.P; p.D = a.D; p.M = a.M;
     p.focal_y = a.H / (2.0f * a.tan_fovy);
@@ -360,7 +387,13 @@ int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum
     p.scales = a.scales; p.rotations = a.rotations; p.cov3D_precomp = a.cov3D_precomp;
     p.view = a.viewmatrix; p.proj = a.projmatrix; p.campos = a.campos;
     p.rec = g.rec; p.accum = reinterpret_cast<const float*>(accum);
-    p.accum_clear = preprocess_bwd_clears_accum() ? reinterpret_cast<float*>(accum) : nullptr;
+    p.accum_clear = (preprocess_bwd_clears_accum() && !pull) ? reinterpret_cast<float*>(accum) : nullptr;
+    p.pull_accums = pull ? pull->accums : nullptr;
+    p.pull_touched = pull ? pull->touched : nullptr;
+    p.pull_n = pull ? pull->n_peers : 0;
+    p.pull_self = pull ? pull->self : 0;
+    p.pull_clear_accum = pull ? pull->clear_accum : nullptr;
+    p.pull_clear_touched = pull ? pull->clear_touched : nullptr;
     p.dL_dmean2D = a.dL_dmean2D; p.dL_dconic = a.dL_dconic; p.dL_dopacity = a.dL_dopacity;
     p.dL_dcolor = a.dL_dcolor; p.dL_dmean3D = a.dL_dmean3D; p.dL_dcov3D = a.dL_dcov3D;
     p.dL_dsh = a.dL_dsh; p.dL_dscale = a.dL_dscale; p.dL_drot = a.dL_drot;

@@ -44,6 +44,7 @@ struct RenderBwdParams {
     float* const* peers;   // [n_peers] device array of the ranks' accumulators mapped into this process, or NULL
     int n_peers;
     float* mc;             // multicast address of the same symmetric buffer, or NULL
+    unsigned char* touched;   // pull-mode reduction: touched[g] = 1 for every Gaussian this rank added to, or NULL
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -75,6 +76,7 @@ __device__ __forceinline__ void flush_row(const RenderBwdParams& p, size_t row, 
         red_add_v4(dst + 0, A.x, A.y, A.z, A.w);
         red_add_v4(dst + 4, B.x, B.y, B.z, B.w);
         red_add_v4(dst + 8, C.x, C.y, C.z, C.w);
+        if (p.touched != nullptr) p.touched[row] = 1;       // benign race: every writer stores the same value
     }
 }
 
@@ -560,8 +562,10 @@ static int bwd_ppt() {
 }
 
 int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinState& b, const ImgState& im,
-                      const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s, const PeerAccum* peer) {
+                      const float* colors, BwdAccum* accum, int ty0, int ty1, cudaStream_t s, const PeerAccum* peer,
+                      unsigned char* touched) {
     RenderBwdParams p;
+    p.touched = touched;
     p.peers = peer ? (float* const*)(peer->peers) : nullptr;
     p.n_peers = peer ? peer->n_peers : 0;
     p.mc = peer ? reinterpret_cast<float*>(peer->multicast) : nullptr;
@@ -583,7 +587,7 @@ int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinSta
         count_launches(1);
         return 0;
     }
-    if (packed) {
+    if (packed || touched) {    // the marks are written by the packed kernel's flush only
         render_bwd_packed_kernel<false><<<grid, 128, 0, s>>>(p);
         count_launches(1);
         return 0;

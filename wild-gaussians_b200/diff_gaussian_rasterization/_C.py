@@ -93,6 +93,10 @@ def _load():
     lib.gsr_backward_partials.argtypes = [POINTER(GsrBackwardArgs), c_void_p]
     lib.gsr_backward_finalize.argtypes = [POINTER(GsrBackwardArgs), c_void_p]
     lib.gsr_backward_partials_peers.argtypes = [POINTER(GsrBackwardArgs), c_void_p, c_int, c_void_p, c_void_p]
+    lib.gsr_backward_partials_marked.argtypes = [POINTER(GsrBackwardArgs), c_void_p, c_void_p]
+    lib.gsr_backward_partials_marked.restype = c_int
+    lib.gsr_backward_finalize_pull.argtypes = [POINTER(GsrBackwardArgs), c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.gsr_backward_finalize_pull.restype = c_int
     lib.gsr_mark_visible.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsr_img_views.argtypes = [c_void_p, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]
     lib.gsr_binning_views.argtypes = [c_void_p, c_int, POINTER(c_void_p)]
@@ -408,7 +412,7 @@ def rasterize_gaussians_shard(shard, background, means3D, colors, opacity, scale
 def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rotations, scale_modifier,
                    cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, kernel_size, subpixel_offset,
                    dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, debug,
-                   want_cov3D=True, peer=None, shard=None):
+                   want_cov3D=True, peer=None, shard=None, marked=None, pull=None):
     """mode: "both" (gsr_backward), "partials" (returns the [P,12] accumulator), "finalize" (consumes it).
     want_cov3D=False (autograd path with scales/rotations): dL_dcov3D is an intermediate nobody reads, so it
     is neither allocated nor written (24 B per Gaussian) and None is returned in its place."""
@@ -470,6 +474,17 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
             a.dL_dsh = _ptr(dL_dsh)
             a.dL_dscale = dL_dscales.data_ptr() if have_scales else None
             a.dL_drot = dL_drotations.data_ptr() if have_scales else None
+        if marked is not None:        # pull-mode first half: local sums + marks
+            a.accum_is_zero = 1
+            _check(_lib.gsr_backward_partials_marked(byref(a), marked.data_ptr(), _stream(dev)), "gsr_backward_partials_marked")
+            return accum
+        if pull is not None:          # pull-mode second half: gather the marked rows of all ranks, chain rule
+            accums_dev, touched_dev, n_peers, self_rank, clear_accum, clear_touched = pull
+            _check(_lib.gsr_backward_finalize_pull(byref(a), int(accums_dev), int(touched_dev), int(n_peers), int(self_rank),
+                                                   None if clear_accum is None else clear_accum.data_ptr(),
+                                                   None if clear_touched is None else clear_touched.data_ptr(), _stream(dev)),
+                   "gsr_backward_finalize_pull")
+            return outs
         if peer is not None:
             peers_dev, n_peers, mc = peer
             _check(_lib.gsr_backward_partials_peers(byref(a), peers_dev or None, int(n_peers), mc or None, _stream(dev)),
@@ -540,6 +555,20 @@ def rasterize_gaussians_backward_partials_peers(accum, peers_dev_ptr, n_peers, m
     NVSwitch multicast address of the buffer or 0."""
     return _backward_impl("partials", accum, *args, peer=(int(peers_dev_ptr), int(n_peers), int(multicast_ptr)),
                           shard=shard)
+
+
+def rasterize_gaussians_backward_partials_marked(accum, touched, *args, shard=None):
+    """Pull-mode first half (``gsr_backward_partials_marked``): this shard's sums go into THIS rank's symmetric accumulator
+    only, ``touched`` (uint8 [P], symmetric) gets a 1 for every Gaussian added to."""
+    return _backward_impl("partials", accum, *args, shard=shard, marked=touched)
+
+
+def rasterize_gaussians_backward_finalize_pull(accum, accums_dev_ptr, touched_dev_ptr, n_peers, self_rank, clear_accum,
+                                               clear_touched, *args, shard=None):
+    """Pull-mode second half (``gsr_backward_finalize_pull``): complete sums = rows of all ranks (peer reads of the marked
+    rows, rank order), chain rule -> the 8 gradient tensors; zeroes the previous pass's marked rows / marks."""
+    return _backward_impl("finalize", accum, *args, want_cov3D=False, shard=shard,
+                          pull=(accums_dev_ptr, touched_dev_ptr, n_peers, self_rank, clear_accum, clear_touched))
 
 
 def rasterize_gaussians_backward_finalize(accum, *args, shard=None):
