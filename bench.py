@@ -500,10 +500,15 @@ def main():
             "data": "synthetic (seeded, SURVEY.md 8d generator)",
             "config": {"workload": workload, "P": P, "W": W, "H": H, "tiles": T,
                        "l2": "inputs_larger_than_l2 (per-step working set >= 0.5 GB vs 126 MB L2)",
-                       "parallelism": "single GPU" if world == 1 else f"tile-row bands x{world}, " + (
-                           "NCCL all-gather (image) + all-reduce (partials)" if os.environ.get("GSR_PEER_REDUCE", "1") == "0" else
-                           "image all-gather fused into the forward composite and partial-gradient reduction fused into the "
-                           "backward composite over NVLink peer memory (symmetric memory; NCCL only for setup)")}}
+                       "parallelism": "single GPU" if world == 1 else f"tile-row bands x{world}, " + {
+                           "0": "NCCL all-gather (image) + all-reduce (partials)",
+                           "1": "image all-gather fused into the forward composite (peer stores) and partial-gradient reduction fused "
+                                "into the backward composite (peer red.add into every rank's accumulator) over NVLink symmetric memory",
+                           "2": "image all-gather fused into the forward composite (peer stores), partial-gradient reduction through "
+                                "the NVSwitch multicast address (multimem.red) from inside the backward composite",
+                           "3": "image all-gather fused into the forward composite (peer stores); backward: local sums + marks, the "
+                                "chain-rule kernel pulls the other ranks' marked rows over NVLink (no remote atomics)",
+                       }.get(os.environ.get("GSR_PEER_REDUCE", "3" if world >= 3 else "1"), "?")}}     # parallel.peer_mode()
 
     sampler = ClockSampler(local_rank)
 

@@ -217,13 +217,15 @@ int    gsr_backward_partials_peers(const GsrBackwardArgs* args, const void* cons
  * (one byte per Gaussian, all-zero on entry).  After a barrier, gsr_backward_finalize_pull forms each Gaussian's complete
  * sums as own row + the rows the other ranks marked, read through their peer-mapped accumulators in rank order 0..n-1
  * (the same order on every rank: the resulting gradients are bit-identical across ranks), and runs the chain rule.
- * peer_accum_dev / peer_touched_dev: DEVICE arrays of n_peers device pointers (entry `self` = this rank's own buffers).
+ * peer_accums / peer_touched: HOST arrays of n_peers (<= GSR_MAX_PULL_PEERS) device pointers -- the ranks' buffers as mapped
+ * into this process (entry `self` = this rank's own buffers).
  * The buffers of THIS pass must stay untouched until every rank has finished reading them, i.e. until the barrier of the
  * next pass: keep two sets and pass the previous pass's set as clear_accum / clear_touched (may be NULL) -- its marked
  * rows and marks are zeroed by this call.                                                                             */
 int    gsr_backward_partials_marked(const GsrBackwardArgs* args, unsigned char* touched, void* stream);
-int    gsr_backward_finalize_pull(const GsrBackwardArgs* args, const void* const* peer_accum_dev,
-                                  const void* const* peer_touched_dev, int n_peers, int self, void* clear_accum,
+#define GSR_MAX_PULL_PEERS 8
+int    gsr_backward_finalize_pull(const GsrBackwardArgs* args, const void* const* peer_accums,
+                                  const void* const* peer_touched, int n_peers, int self, void* clear_accum,
                                   unsigned char* clear_touched, void* stream);
 
 /* -- markVisible (rasterizer_impl.cu:54-66,141-153): present[i] = (view*p).z > 0.2 ------- */

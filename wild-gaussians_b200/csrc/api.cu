@@ -517,7 +517,8 @@ int gsr_backward_finalize_pull(const GsrBackwardArgs* a, const void* const* peer
                                int n_peers, int self, void* clear_accum, unsigned char* clear_touched, void* stream) {
     int rc = check_bwd_args(a, false, true);
     if (rc || a->P == 0) return rc;
-    if (!peer_accum_dev || !peer_touched_dev || n_peers <= 0 || self < 0 || self >= n_peers || ((clear_accum == nullptr) != (clear_touched == nullptr))) {
+    if (!peer_accum_dev || !peer_touched_dev || n_peers <= 0 || n_peers > GSR_MAX_PULL_PEERS || self < 0 || self >= n_peers ||
+        ((clear_accum == nullptr) != (clear_touched == nullptr))) {
         set_error("gsr_backward_finalize_pull: bad peer arguments");
         return GSR_E_INVALID;
     }

@@ -156,8 +156,8 @@ int launch_render_bwd(const GsrBackwardArgs& a, const GeomState& g, const BinSta
                       const PeerAccum* peer = nullptr, unsigned char* touched = nullptr);
 // pull-mode reduction (render_bwd marks, preprocess_bwd gathers the marked rows of the other ranks): see gsrast.h
 struct PullPeers {
-    const float* const* accums;          // device array [n_peers] of accumulator pointers (peer-mapped)
-    const unsigned char* const* touched; // device array [n_peers] of mark arrays
+    const float* const* accums;          // HOST array [n_peers] of accumulator pointers (peer-mapped device addresses)
+    const unsigned char* const* touched; // HOST array [n_peers] of mark arrays
     int n_peers, self;
     float* clear_accum;                  // previous pass's own accumulator / marks to zero, or NULL
     unsigned char* clear_touched;

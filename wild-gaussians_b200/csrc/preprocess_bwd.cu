@@ -35,9 +35,9 @@ struct PreBwdParams {
     const float* accum;     // [P][12]
     float* accum_clear;     // the same array when the kernel is to zero the rows it consumed (see launch_preprocess_bwd), else NULL
     // pull-mode multi-GPU reduction (gsrast.h, gsr_backward_finalize_pull): complete sums = rows of all ranks in rank order
-    const float* const* pull_accums;          // device array [pull_n] of the ranks' accumulators, or NULL
-    const unsigned char* const* pull_touched; // device array [pull_n] of the ranks' mark arrays
-    int pull_n, pull_self;
+    const float* pull_accums[GSR_MAX_PULL_PEERS];            // the ranks' accumulators (peer-mapped), by value: no pointer-table load
+    const unsigned char* pull_touched[GSR_MAX_PULL_PEERS];   // the ranks' mark arrays
+    int pull_n, pull_self;                                   // pull_n == 0: single-accumulator mode
     float* pull_clear_accum;                  // previous pass's own accumulator: rows marked in pull_clear_touched are zeroed
     unsigned char* pull_clear_touched;
     float* dL_dmean2D;      // [P,3]
@@ -147,12 +147,18 @@ __global__ void __launch_bounds__(256, MIN_CTAS) preprocess_bwd_kernel(const __g
     // A visible Gaussian that no pixel blended (occluded, or alpha < 1/255 everywhere: most of a dense scene) has an
     // all-zero row of sums: every gradient of it is zero, so its inputs are not even read.
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
-    if (p.pull_accums != nullptr) {
+    if (p.pull_n > 0) {
         // rows of all ranks, added in rank order (identical on every rank -> bit-identical gradients everywhere); a rank that
-        // did not mark the Gaussian contributes an all-zero row, which is skipped (x + 0 = x) without reading it
+        // did not mark the Gaussian contributes an all-zero row, which is skipped (x + 0 = x) without reading it.  All marks
+        // are requested first (independent remote loads: one NVLink round trip, not one per rank).
         if (rendered) {
-            for (int r = 0; r < p.pull_n; ++r) {
-                if (r != p.pull_self && p.pull_touched[r][idx] == 0) continue;
+            unsigned char mark[GSR_MAX_PULL_PEERS];
+#pragma unroll
+            for (int r = 0; r < GSR_MAX_PULL_PEERS; ++r)
+                mark[r] = (r < p.pull_n && r != p.pull_self) ? p.pull_touched[r][idx] : (unsigned char)(r == p.pull_self);
+#pragma unroll
+            for (int r = 0; r < GSR_MAX_PULL_PEERS; ++r) {
+                if (r >= p.pull_n || mark[r] == 0) continue;
                 const float4* acc = reinterpret_cast<const float4*>((r == p.pull_self ? p.accum : p.pull_accums[r]) + (size_t)idx * 12);
                 const float4 b0 = acc[0], b1 = acc[1], b2 = acc[2];
                 a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
@@ -388,8 +394,10 @@ int launch_preprocess_bwd(const GsrBackwardArgs& a, const GeomState& g, BwdAccum
     p.view = a.viewmatrix; p.proj = a.projmatrix; p.campos = a.campos;
     p.rec = g.rec; p.accum = reinterpret_cast<const float*>(accum);
     p.accum_clear = (preprocess_bwd_clears_accum() && !pull) ? reinterpret_cast<float*>(accum) : nullptr;
-    p.pull_accums = pull ? pull->accums : nullptr;
-    p.pull_touched = pull ? pull->touched : nullptr;
+    for (int r = 0; r < GSR_MAX_PULL_PEERS; ++r) {
+        p.pull_accums[r] = (pull && r < pull->n_peers) ? pull->accums[r] : nullptr;
+        p.pull_touched[r] = (pull && r < pull->n_peers) ? pull->touched[r] : nullptr;
+    }
     p.pull_n = pull ? pull->n_peers : 0;
     p.pull_self = pull ? pull->self : 0;
     p.pull_clear_accum = pull ? pull->clear_accum : nullptr;

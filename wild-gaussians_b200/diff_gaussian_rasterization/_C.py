@@ -479,8 +479,10 @@ def _backward_impl(mode, accum, background, means3D, radii, colors, scales, rota
             _check(_lib.gsr_backward_partials_marked(byref(a), marked.data_ptr(), _stream(dev)), "gsr_backward_partials_marked")
             return accum
         if pull is not None:          # pull-mode second half: gather the marked rows of all ranks, chain rule
-            accums_dev, touched_dev, n_peers, self_rank, clear_accum, clear_touched = pull
-            _check(_lib.gsr_backward_finalize_pull(byref(a), int(accums_dev), int(touched_dev), int(n_peers), int(self_rank),
+            accum_ptrs, touched_ptrs, n_peers, self_rank, clear_accum, clear_touched = pull
+            arr_a = (c_void_p * int(n_peers))(*[int(x) for x in accum_ptrs])
+            arr_t = (c_void_p * int(n_peers))(*[int(x) for x in touched_ptrs])
+            _check(_lib.gsr_backward_finalize_pull(byref(a), arr_a, arr_t, int(n_peers), int(self_rank),
                                                    None if clear_accum is None else clear_accum.data_ptr(),
                                                    None if clear_touched is None else clear_touched.data_ptr(), _stream(dev)),
                    "gsr_backward_finalize_pull")
@@ -563,12 +565,12 @@ def rasterize_gaussians_backward_partials_marked(accum, touched, *args, shard=No
     return _backward_impl("partials", accum, *args, shard=shard, marked=touched)
 
 
-def rasterize_gaussians_backward_finalize_pull(accum, accums_dev_ptr, touched_dev_ptr, n_peers, self_rank, clear_accum,
+def rasterize_gaussians_backward_finalize_pull(accum, accum_ptrs, touched_ptrs, n_peers, self_rank, clear_accum,
                                                clear_touched, *args, shard=None):
     """Pull-mode second half (``gsr_backward_finalize_pull``): complete sums = rows of all ranks (peer reads of the marked
     rows, rank order), chain rule -> the 8 gradient tensors; zeroes the previous pass's marked rows / marks."""
     return _backward_impl("finalize", accum, *args, want_cov3D=False, shard=shard,
-                          pull=(accums_dev_ptr, touched_dev_ptr, n_peers, self_rank, clear_accum, clear_touched))
+                          pull=(accum_ptrs, touched_ptrs, n_peers, self_rank, clear_accum, clear_touched))
 
 
 def rasterize_gaussians_backward_finalize(accum, *args, shard=None):

@@ -99,7 +99,16 @@ def reduce_partials(accum: torch.Tensor, group=None) -> torch.Tensor:
 # one barrier every rank's chain-rule kernel reads the marked rows of the other ranks through their peer mappings (plain
 # loads, rank order -> bit-identical gradients on all ranks).  No remote atomics: peer `red` is posted cheaply but drains
 # slowly (measured at 4 GPUs: 0.37 ms of the 1.21-ms step are hidden behind the barrier that follows the kernel).
-_PEER_MODE = int(os.environ.get("GSR_PEER_REDUCE", "1"))
+# Default (GSR_PEER_REDUCE unset): 1 for two ranks, 3 from three ranks on -- measured on B200s at C3: 2 GPUs 1.12 ms (mode 1) vs
+# 1.19 (mode 3); 4 GPUs 1.21 (mode 1) vs 0.92 (mode 2) vs 0.91 (mode 3).
+_PEER_MODE_ENV = os.environ.get("GSR_PEER_REDUCE")
+
+
+def peer_mode(group=None) -> int:
+    """The reduction mode in effect for this process group (see above)."""
+    if _PEER_MODE_ENV is not None:
+        return int(_PEER_MODE_ENV)
+    return 3 if dist.get_world_size(group) >= 3 else 1
 _peer_state: dict = {}
 _peer_warned = False
 
@@ -110,6 +119,7 @@ class _PeerState:
     def __init__(self, P, H, W, device, group):
         import torch.distributed._symmetric_memory as symm_mem
         g = group if group is not None else dist.group.WORLD
+        mode = peer_mode(group)
         # two accumulators, used alternately (same argument as for the images below: with several backward passes per
         # step -- wild-gaussians composites twice -- a rank's reductions of pass k+1 must not land in a peer's accumulator
         # while that peer is still consuming pass k; pass k+2 lies behind pass k+1's barrier)
@@ -120,7 +130,7 @@ class _PeerState:
         self.bwd = 0
         # pull-mode reduction (GSR_PEER_REDUCE=3): one mark byte per Gaussian next to each accumulator
         self.marks, self.mark_hdls = [], []
-        if _PEER_MODE == 3:
+        if mode == 3:
             self.marks = [symm_mem.empty(P + 256, dtype=torch.uint8, device=device) for _ in range(2)]
             for t in self.marks:
                 t.zero_()
@@ -132,7 +142,7 @@ class _PeerState:
         self.image_hdls = [symm_mem.rendezvous(t, g) for t in self.images]
         self.frame = 0
         self.mcs = [0, 0]
-        if _PEER_MODE == 2:
+        if mode == 2:
             for i, h in enumerate(self.accum_hdls):
                 try:
                     self.mcs[i] = int(h.multicast_ptr or 0)
@@ -148,7 +158,7 @@ class _PeerState:
 def _peers(P, H, W, device, group):
     """The symmetric state, or None when the NCCL path has to be used."""
     global _peer_warned
-    if _PEER_MODE <= 0 or P <= 0 or dist.get_backend(group) != "nccl":
+    if peer_mode(group) <= 0 or P <= 0 or dist.get_backend(group) != "nccl":
         return None
     key = (int(P), int(H), int(W), str(device), id(group))
     st = _peer_state.get(key)
@@ -217,7 +227,7 @@ def sharded_backward(bwd_args, bands, group=None):
     rank = dist.get_rank(group)
     means3D = bwd_args[1]
     shard = tuple(bands[rank])
-    if _PEER_MODE == 3:
+    if peer_mode(group) == 3:
         P = int(means3D.size(0))
         H, W = int(bwd_args[14].size(1)), int(bwd_args[14].size(2))
         st = _peers(P, H, W, means3D.device, group)
@@ -230,7 +240,7 @@ def sharded_backward(bwd_args, bands, group=None):
             _C.rasterize_gaussians_backward_partials_marked(accum, marks, *bwd_args, shard=shard)
             hdl.barrier(channel=1)               # every rank's sums and marks of this pass are complete
             return _C.rasterize_gaussians_backward_finalize_pull(
-                accum, hdl.buffer_ptrs_dev, mhdl.buffer_ptrs_dev, st.world, hdl.rank, st.accums[k ^ 1], st.marks[k ^ 1],
+                accum, list(hdl.buffer_ptrs), list(mhdl.buffer_ptrs), st.world, hdl.rank, st.accums[k ^ 1], st.marks[k ^ 1],
                 *bwd_args, shard=shard)
     accum = reduced_partials(bwd_args, int(means3D.size(0)), means3D.device, group, shard=shard)
     return _C.rasterize_gaussians_backward_finalize(accum, *bwd_args, shard=shard)
