@@ -670,9 +670,14 @@ def main():
                             "frac": stages[dom]["gbs"] / peak, "traffic": ncu_traffic(dom, a.config), "peak_source": peak_src,
                             "alg_bytes_per_launch": stages[dom]["alg_bytes"], "launch_ms": stages[dom]["ms"]}
         Bf, Bb = path_bytes(P, V, R, N, sh_M)
+        # second reading: the formula charges R * (36 + 40) B of per-instance delivery, but only `visited` of the R list
+        # entries are ever walked before the pixels saturate (the rest is never read): delivery terms with `visited`
+        Bw = (Bf - R * 36 + visited * 36) + (Bb - R * 40 + visited * 40)
         line["roofline_path"] = {"bound": "hbm", "B_fwd": int(Bf), "B_bwd": int(Bb), "achieved": (Bf + Bb) / (ms * 1e-3) / 1e9,
                                  "peak": peak, "unit": "GB/s", "frac": (Bf + Bb) / (ms * 1e-3) / 1e9 / peak,
-                                 "formula": "SURVEY.md 8(d)"}
+                                 "formula": "SURVEY.md 8(d)",
+                                 "bytes_with_walked_instances": int(Bw),
+                                 "frac_with_walked_instances": Bw / (ms * 1e-3) / 1e9 / peak}
     else:
         # rank 0's stages against the per-GPU HBM peak (rank-local algorithmic bytes: its band's instances and
         # pixels, all P Gaussians for the replicated per-Gaussian stages); whole-path figure against N x peak

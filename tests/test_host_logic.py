@@ -89,3 +89,28 @@ def test_fused_entry_points_reject_cpu_tensors_without_a_gpu():
                         torch.zeros(3), 3)
     with pytest.raises(RuntimeError, match="CUDA"):
         fc.fused_activations(torch.zeros(4, 3), torch.zeros(4, 1), torch.zeros(4, 4), torch.zeros(4, 1))
+
+
+def test_reduction_mode_default_depends_on_world_size(monkeypatch):
+    """parallel.peer_mode(): peer `red` for two ranks, the pull form from three ranks on; GSR_PEER_REDUCE overrides."""
+    import parallel
+    import torch.distributed as dist
+    monkeypatch.setattr(parallel, "_PEER_MODE_ENV", None)
+    for world, want in ((2, 1), (3, 3), (4, 3), (8, 3)):
+        monkeypatch.setattr(dist, "get_world_size", lambda group=None, w=world: w)
+        assert parallel.peer_mode() == want
+    monkeypatch.setattr(parallel, "_PEER_MODE_ENV", "0")
+    assert parallel.peer_mode() == 0
+
+
+def test_pull_mode_entry_points_reject_bad_arguments():
+    """gsr_backward_partials_marked / gsr_backward_finalize_pull validate their arguments before touching CUDA."""
+    import ctypes
+    import diff_gaussian_rasterization._C as C
+    a = C.GsrBackwardArgs()
+    a.P = 10
+    assert C._lib.gsr_backward_partials_marked(ctypes.byref(a), None, None) != 0            # touched is NULL
+    assert b"touched" in C._lib.gsr_last_error()
+    arr = (ctypes.c_void_p * 9)()
+    a.P, a.W, a.H = 0, 16, 16
+    assert C._lib.gsr_backward_finalize_pull(ctypes.byref(a), arr, arr, 2, 0, None, None, None) == 0     # P == 0: nothing to do
