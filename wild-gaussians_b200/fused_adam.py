@@ -78,13 +78,14 @@ class FusedAdam(torch.optim.Adam):
                     part = items[i:i + _C.ADAM_MAX_SEGMENTS]
                     segs = (_C.GsrAdamSegment * len(part))()
                     for s, (group, p, state) in zip(segs, part):
-                        state["step"] += 1                  # a CPU scalar tensor, like torch keeps it
                         s.param, s.grad = p.data_ptr(), p.grad.data_ptr()
                         s.exp_avg, s.exp_avg_sq = state["exp_avg"].data_ptr(), state["exp_avg_sq"].data_ptr()
-                        s.n, s.step = p.numel(), int(state["step"].item())
+                        s.n, s.step = p.numel(), int(state["step"].item()) + 1      # the count AFTER this update
                         s.lr, s.weight_decay = float(group["lr"]), float(group["weight_decay"])
                     _C._check(_C._lib.gsr_adam_step(segs, len(part), beta1, beta2, eps, int(bool(self.zero_grads_in_step)),
                                                     ctypes.c_void_p(stream)), "gsr_adam_step")
+                    for _, _, state in part:                # only once the launch was accepted
+                        state["step"] += 1                  # a CPU scalar tensor, like torch keeps it
         return None
 
 
