@@ -1,5 +1,8 @@
 #!/bin/bash
-# multi-GPU session.  usage: bash tools/gpu_scale.sh TAG N [N2 ...]   (run under gpurun --gpus max(N))
+# multi-GPU session.  usage: bash tools/gpu_scale.sh TAG N [N2 ...]   (run under gpurun --gpus max(N)): one default bench line per N.
+# Sourced (`source tools/gpu_scale.sh TAG`) it only defines `run NAME N [ENV=..]... -- bench-args`, e.g. the sessions of round 2:
+#   run c3_4gpu_pull 4 GSR_PEER_REDUCE=3 -- --no-train-step --no-other-configs --no-cpu-baseline
+#   run c5_8gpu 8 GSR_DUMMY=0 -- --config C5 --no-train-step --no-other-configs --no-cpu-baseline --no-e2e --steps 10
 TAG=$1; shift
 mkdir -p gpurun_out
 run() {  # run NAME N [env...] -- bench args
